@@ -1,0 +1,73 @@
+"""CPU oracle: Philox4x32-10 counter RNG and the eps ~ N(0,1) stream the CUDA
+reparameterisation kernel draws from.  TEST INFRASTRUCTURE ONLY.
+
+The reference draws eps with torch.randn_like (vanilla_vae.py:39) from the
+global generator, which no other implementation can reproduce; the B200 path
+replaces it by a counter-based stream keyed by (seed, offset, element index)
+so that forward and backward regenerate the same eps without storing it.
+This file is the host restatement of that stream (numpy, vectorised):
+
+  Philox4x32-10: Salmon, Moraes, Dror, Shaw, "Parallel random numbers: as easy
+  as 1, 2, 3" (SC'11); constants M0=0xD2511F53, M1=0xCD9E8D57,
+  W0=0x9E3779B9, W1=0xBB67AE85.  Known-answer vectors from the Random123
+  distribution (kat_vectors) are checked in tests/test_philox.py.
+
+  Element i of the stream (flat, row-major index into the (M, L) latent):
+    block   q = i // 4, lane r = i % 4
+    counter = (q & 0xffffffff, q >> 32, offset & 0xffffffff, offset >> 32)
+    key     = (seed & 0xffffffff, seed >> 32)
+    u32[4]  = philox4x32_10(counter, key)
+    Box-Muller on pairs: (u32[0], u32[1]) -> normals 0,1 ; (u32[2], u32[3]) -> 2,3
+      u1 = (a + 1) * 2^-32          in (0, 1]
+      u2 = b * 2^-32                in [0, 1)
+      rad = sqrt(-2 ln u1);  n_even = rad * cos(2 pi u2);  n_odd = rad * sin(2 pi u2)
+"""
+from __future__ import annotations
+
+import numpy as np
+
+M0 = np.uint64(0xD2511F53)
+M1 = np.uint64(0xCD9E8D57)
+W0 = 0x9E3779B9
+W1 = 0xBB67AE85
+MASK = np.uint64(0xFFFFFFFF)
+
+
+def philox4x32_10(ctr: np.ndarray, key: np.ndarray) -> np.ndarray:
+    """ctr (..., 4) uint32, key (..., 2) uint32 -> (..., 4) uint32."""
+    c = [ctr[..., i].astype(np.uint64) for i in range(4)]
+    k0 = key[..., 0].astype(np.uint64)
+    k1 = key[..., 1].astype(np.uint64)
+    for _ in range(10):
+        p0 = M0 * c[0]
+        p1 = M1 * c[2]
+        hi0, lo0 = p0 >> np.uint64(32), p0 & MASK
+        hi1, lo1 = p1 >> np.uint64(32), p1 & MASK
+        c = [(hi1 ^ c[1] ^ k0) & MASK, lo1, (hi0 ^ c[3] ^ k1) & MASK, lo0]
+        k0 = (k0 + np.uint64(W0)) & MASK
+        k1 = (k1 + np.uint64(W1)) & MASK
+    return np.stack(c, axis=-1).astype(np.uint32)
+
+
+def philox_u32(seed: int, offset: int, n: int) -> np.ndarray:
+    """First n uint32 of the element stream described in the module docstring."""
+    nblk = (n + 3) // 4
+    q = np.arange(nblk, dtype=np.uint64)
+    ctr = np.stack([q & MASK, q >> np.uint64(32),
+                    np.full(nblk, offset & 0xFFFFFFFF, np.uint64),
+                    np.full(nblk, (offset >> 32) & 0xFFFFFFFF, np.uint64)], -1).astype(np.uint32)
+    key = np.empty((nblk, 2), np.uint32)
+    key[:, 0] = seed & 0xFFFFFFFF
+    key[:, 1] = (seed >> 32) & 0xFFFFFFFF
+    return philox4x32_10(ctr, key).reshape(-1)[:n]
+
+
+def philox_normal(seed: int, offset: int, n: int, dtype=np.float32) -> np.ndarray:
+    """eps stream, computed in float64 and rounded once to ``dtype``."""
+    nblk = (n + 3) // 4
+    u = philox_u32(seed, offset, nblk * 4).reshape(nblk, 2, 2).astype(np.float64)
+    u1 = (u[..., 0] + 1.0) * 2.0 ** -32
+    u2 = u[..., 1] * 2.0 ** -32
+    rad = np.sqrt(-2.0 * np.log(u1))
+    out = np.stack([rad * np.cos(2.0 * np.pi * u2), rad * np.sin(2.0 * np.pi * u2)], -1)
+    return out.reshape(-1)[:n].astype(dtype)
