@@ -1,0 +1,180 @@
+/*
+ * mlvae_b200.h -- C ABI of libmlvae_b200.so: the B200 (sm_100a) kernels behind the
+ * ML-VAE data-parallel training hot path.
+ *
+ * Boundary rules
+ *   - extern "C", plain pointers and sizes only; no torch / C++ types.
+ *   - every pointer named d_* is a DEVICE pointer on the current CUDA device;
+ *     `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - every entry point returns MLVAE_OK (0) or a negative mlvae_status; nothing
+ *     throws across the ABI.  mlvae_last_error() gives the text for the calling thread.
+ *   - no entry point allocates device memory behind the caller's back except
+ *     mlvae_fbank_plan_create (small constant tables, freed by _destroy); scratch
+ *     buffers are caller-owned and sized by the *_scratch_bytes() helpers.
+ *   - launches are asynchronous on `stream`; the caller owns synchronisation.
+ *   - there is no CPU fallback anywhere behind this interface.
+ *
+ * Each function names the reference interface it replaces (paths relative to
+ * the reference checkout, weiwei-ww/ML-VAE).  INTEGRATION.md shows the ctypes
+ * binding and the yaml change a reference maintainer would make.
+ */
+#ifndef MLVAE_B200_H_
+#define MLVAE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MLVAE_ABI_VERSION 1
+
+typedef enum mlvae_status {
+    MLVAE_OK = 0,
+    MLVAE_ERR_INVALID_ARG = -1, /* null pointer, negative size, misaligned buffer */
+    MLVAE_ERR_UNSUPPORTED = -2, /* configuration outside what the kernels implement */
+    MLVAE_ERR_CUDA = -3,        /* CUDA runtime / launch error (text in mlvae_last_error) */
+    MLVAE_ERR_NO_DEVICE = -4    /* no sm_100 device visible */
+} mlvae_status;
+
+typedef enum mlvae_dtype {
+    MLVAE_F32 = 0,
+    MLVAE_BF16 = 1
+} mlvae_dtype;
+
+/* reduction argument of utils/data_utils.py:67 apply_lens_to_loss */
+typedef enum mlvae_reduction {
+    MLVAE_RED_MEAN = 0,      /* sum(loss*mask) / sum(mask)               -> out[1] */
+    MLVAE_RED_BATCHMEAN = 1, /* sum(loss*mask) / B                       -> out[1] */
+    MLVAE_RED_BATCH = 2      /* per row b: sum_b(loss*mask)/sum_b(mask)  -> out[B] */
+} mlvae_reduction;
+
+/* loss_type argument of modules/decoder.py:11 Decoder(...) */
+typedef enum mlvae_recon_type {
+    MLVAE_RECON_LIKELIHOOD = 0, /* decoder.py:40-43 Gaussian NLL, eps = 1e-5 */
+    MLVAE_RECON_MSE = 1         /* decoder.py:48-49 */
+} mlvae_recon_type;
+
+int mlvae_abi_version(void);
+const char *mlvae_last_error(void);
+/* number of SMs / compute capability major*10+minor of the current device */
+int mlvae_device_info(int *sm_count, int *cc);
+
+/* Bytes of caller-owned scratch every *_fwd reduction below needs.  The buffer
+ * must be zero-filled ONCE after allocation (the kernels leave it zeroed). */
+size_t mlvae_reduce_scratch_bytes(void);
+
+/* ------------------------------------------------------------------------- *
+ * Counter-based eps (replaces torch.randn_like at modules/vanilla_vae.py:39).
+ * Stream definition: oracle/philox_ref.py.  Element i of the stream uses
+ * Philox4x32-10 counter (i/4, offset), key seed; the same (seed, offset) in
+ * _fwd and _bwd regenerates the same eps without storing it.
+ * ------------------------------------------------------------------------- */
+int mlvae_philox_u32(uint64_t seed, uint64_t offset, int64_t n, uint32_t *d_out, void *stream);
+int mlvae_philox_normal(uint64_t seed, uint64_t offset, int64_t n, void *d_out, int dtype, void *stream);
+
+/* ------------------------------------------------------------------------- *
+ * Fused reparameterise + KL (+ length-masked mean).
+ * Replaces VanillaVAE.reparameterize (modules/vanilla_vae.py:37-40),
+ * VanillaVAE.compute_kld_loss (:42-45) and, when d_kl_out != NULL, the
+ * apply_lens_to_loss(.., 'mean') over it (utils/data_utils.py:67-104).
+ *
+ *   z        = mu + exp(0.5*logvar) * eps
+ *   kl       = -0.5 * (1 + logvar - mu^2 - exp(logvar))              (B,T,L)
+ *   mask     = float(t) < d_lens[b] * T   (float32, no rounding)
+ *   d_kl_out = { sum(kl*mask) / (count*L), sum(kl*mask), count*L }     float[3]
+ *
+ * d_mu, d_logvar, d_z, d_kl_elem: (B,T,L) contiguous, element type `dtype`.
+ * d_eps: same shape/dtype, or NULL to draw from Philox(seed, offset).
+ * d_kl_elem (unreduced KL, the reference module contract) may be NULL.
+ * d_kl_out may be NULL (then d_lens and d_scratch may be NULL too).
+ * ------------------------------------------------------------------------- */
+int mlvae_reparam_kl_fwd(const void *d_mu, const void *d_logvar, const void *d_eps,
+                         uint64_t seed, uint64_t offset, const float *d_lens,
+                         int B, int T, int L, int dtype,
+                         void *d_z, void *d_kl_elem, float *d_kl_out, void *d_scratch,
+                         void *stream);
+
+/*   g_elem   = d_grad_kl_elem (may be NULL) + d_grad_kl_mean[0] * mask / (count*L) (may be NULL)
+ *   grad_mu     = grad_z + g_elem * mu
+ *   grad_logvar = grad_z * 0.5*exp(0.5*logvar)*eps + g_elem * 0.5*(exp(logvar) - 1)
+ * d_grad_z may be NULL (treated as zero).  d_grad_kl_mean is a DEVICE float scalar. */
+int mlvae_reparam_kl_bwd(const void *d_mu, const void *d_logvar, const void *d_eps,
+                         uint64_t seed, uint64_t offset, const void *d_grad_z,
+                         const void *d_grad_kl_elem, const float *d_grad_kl_mean,
+                         const float *d_lens, int B, int T, int L, int dtype,
+                         void *d_grad_mu, void *d_grad_logvar, void *stream);
+
+/* ------------------------------------------------------------------------- *
+ * Fused reconstruction loss (+ length-masked mean).
+ * Replaces Decoder.compute_recon_loss (modules/decoder.py:37-53) and the
+ * apply_lens_to_loss over it (models/test_vanilla_vae/model.py:50).
+ *   likelihood: 0.5*(log(2*pi)_f32 + logvar + (target-mean)^2 / (exp(logvar) + 1e-5))
+ *   mse:        (target-mean)^2            (d_logvar ignored, may be NULL)
+ * d_out = { masked mean, masked sum, count*D }  float[3]; d_elem may be NULL.
+ * ------------------------------------------------------------------------- */
+int mlvae_recon_fwd(const void *d_mean, const void *d_logvar, const void *d_target,
+                    const float *d_lens, int B, int T, int D, int dtype, int loss_type,
+                    void *d_elem, float *d_out, void *d_scratch, void *stream);
+
+/* g_elem as above.  d_grad_target may be NULL (the reference never needs it:
+ * target is the un-learned feature tensor).  d_grad_logvar is ignored for mse. */
+int mlvae_recon_bwd(const void *d_mean, const void *d_logvar, const void *d_target,
+                    const void *d_grad_elem, const float *d_grad_mean_scalar,
+                    const float *d_lens, int B, int T, int D, int dtype, int loss_type,
+                    void *d_grad_mean, void *d_grad_logvar, void *d_grad_target, void *stream);
+
+/* ------------------------------------------------------------------------- *
+ * Stand-alone length-masked reduction = utils/data_utils.py:67-104
+ * apply_lens_to_loss(loss (B,T,C), lens (B,), reduction) for callers that keep
+ * the reference's unreduced-loss module contract.
+ * d_out: float[1] (mean, batchmean) or float[B] (batch).
+ * ------------------------------------------------------------------------- */
+int mlvae_masked_reduce_fwd(const void *d_loss, const float *d_lens, int B, int T, int C,
+                            int dtype, int reduction, float *d_out, void *d_scratch, void *stream);
+int mlvae_masked_reduce_bwd(const float *d_grad_out, const float *d_lens, int B, int T, int C,
+                            int dtype, int reduction, void *d_grad_loss, void *stream);
+
+/* ------------------------------------------------------------------------- *
+ * Fused acoustic front-end = speechbrain.lobes.features.Fbank as declared at
+ * config/run.yaml:39-44 and called at utils/data_io.py:197-201
+ * (framing, Hamming window, 400-point real FFT, power, triangular mel bank,
+ *  10*log10, per-utterance top_db=80 floor, optional delta / delta-delta,
+ *  optional Kaldi-length truncation, zero padding past each utterance).
+ * Only the reference's geometry is implemented: win_length == n_fft == 400.
+ * ------------------------------------------------------------------------- */
+typedef struct mlvae_fbank_plan mlvae_fbank_plan;
+
+/* h_window: 400 host floats or NULL (periodic Hamming computed internally).
+ * h_melmat: (n_fft/2+1) x n_mels row-major host floats or NULL (SpeechBrain
+ * triangular construction computed internally in float32). */
+int mlvae_fbank_plan_create(mlvae_fbank_plan **plan, int sample_rate, int hop_samples, int n_fft,
+                            int n_mels, int deltas, const float *h_window, const float *h_melmat);
+int mlvae_fbank_plan_destroy(mlvae_fbank_plan *plan);
+/* frames emitted for an utterance of n samples: full = 1 + n/hop; kept =
+ * min(full, (n + hop/2)/hop)  (data_io.py:198-201, data_io_utils.py:156) */
+int mlvae_fbank_frames(const mlvae_fbank_plan *plan, int64_t n_samples, int truncate_kaldi);
+int mlvae_fbank_feature_dim(const mlvae_fbank_plan *plan);
+size_t mlvae_fbank_scratch_bytes(const mlvae_fbank_plan *plan, int B, int64_t n_max);
+
+/* d_wav: (B, n_stride) float32, row b valid for d_wav_len[b] samples (int32
+ * device array; NULL = every row is n_max samples).  d_out: (B, t_out, D) of
+ * `out_dtype`, rows past each utterance's frame count are written as zeros.
+ * d_out_frames: int32[B] frames written per utterance (may be NULL). */
+int mlvae_fbank_fwd(const mlvae_fbank_plan *plan, const float *d_wav, const int32_t *d_wav_len,
+                    int B, int64_t n_max, int64_t n_stride, int truncate_kaldi,
+                    void *d_out, int out_dtype, int t_out, int32_t *d_out_frames,
+                    void *d_scratch, void *stream);
+
+/* ------------------------------------------------------------------------- *
+ * tcgen05 / TMEM fused dense stack (modules/fc_block.py:4-21 and the
+ * mean/log_var heads of vanilla_vae.py:22-24 and decoder.py:24-25).
+ * Declared in mlvae_b200_gemm.h once the kernel lands; round 1 routes the
+ * projections through cuBLAS (library) and says so in DESIGN.md.
+ * ------------------------------------------------------------------------- */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MLVAE_B200_H_ */

@@ -1,0 +1,109 @@
+"""ctypes binding of libmlvae_b200.so (include/mlvae_b200.h).
+
+The library is the product; there is no Python/torch fallback.  Loading fails
+loudly when the .so is missing, and every compute entry point raises when it is
+handed a non-CUDA tensor.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libmlvae_b200.so")
+
+F32, BF16 = 0, 1
+RED = {"mean": 0, "batchmean": 1, "batch": 2}
+RECON = {"likelihood": 0, "mse": 1}
+
+_vp, _i, _i64, _u64, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_size_t
+
+# name -> (restype, argtypes); mirrors include/mlvae_b200.h one to one
+SIGNATURES = {
+    "mlvae_abi_version": (_i, []),
+    "mlvae_last_error": (C.c_char_p, []),
+    "mlvae_device_info": (_i, [C.POINTER(_i), C.POINTER(_i)]),
+    "mlvae_reduce_scratch_bytes": (_sz, []),
+    "mlvae_philox_u32": (_i, [_u64, _u64, _i64, _vp, _vp]),
+    "mlvae_philox_normal": (_i, [_u64, _u64, _i64, _vp, _i, _vp]),
+    "mlvae_reparam_kl_fwd": (_i, [_vp, _vp, _vp, _u64, _u64, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "mlvae_reparam_kl_bwd": (_i, [_vp, _vp, _vp, _u64, _u64, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "mlvae_recon_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "mlvae_recon_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "mlvae_masked_reduce_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "mlvae_masked_reduce_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "mlvae_fbank_plan_create": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _i, _vp, _vp]),
+    "mlvae_fbank_plan_destroy": (_i, [_vp]),
+    "mlvae_fbank_frames": (_i, [_vp, _i64, _i]),
+    "mlvae_fbank_feature_dim": (_i, [_vp]),
+    "mlvae_fbank_scratch_bytes": (_sz, [_vp, _i, _i64]),
+    "mlvae_fbank_fwd": (_i, [_vp, _vp, _vp, _i, _i64, _i64, _i, _vp, _i, _i, _vp, _vp, _vp]),
+}
+
+_lib = None
+
+
+class MlvaeError(RuntimeError):
+    pass
+
+
+def lib() -> C.CDLL:
+    """Load (once) and type the shared library.  No fallback: a missing library is an error."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise MlvaeError(
+                f"{LIB_PATH} is missing: build it with `python -m ml_vae_b200.build` "
+                "(nvcc, sm_100a).  ml_vae_b200 has no CPU or PyTorch fallback.")
+        h = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(h, name, None)
+            if fn is None:
+                continue        # optional extension headers (gemm / lstm) bind their own symbols
+            fn.restype, fn.argtypes = res, args
+        _lib = h
+    return _lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = lib().mlvae_last_error()
+        raise MlvaeError(f"{what} failed with status {rc}: {msg.decode() if msg else ''}")
+
+
+def dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise MlvaeError(f"unsupported dtype {t.dtype}: the B200 kernels take float32 or bfloat16")
+
+
+def ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise MlvaeError("ml_vae_b200 runs on CUDA tensors only (no CPU fallback); got a tensor on "
+                             f"{t.device}")
+
+
+def stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+_scratch = {}
+
+
+def reduce_scratch(device, slot: int = 0) -> torch.Tensor:
+    """Zero-initialised, self-resetting reduction scratch; one per (device, stream, slot)."""
+    key = (device, torch.cuda.current_stream(device).cuda_stream, slot)
+    buf = _scratch.get(key)
+    if buf is None:
+        buf = torch.zeros(lib().mlvae_reduce_scratch_bytes(), dtype=torch.uint8, device=device)
+        _scratch[key] = buf
+    return buf

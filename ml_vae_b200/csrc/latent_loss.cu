@@ -1,0 +1,589 @@
+// Fused latent-block loss kernels for sm_100a:
+//   reparameterise + KL (+ masked mean)   fwd / bwd     vanilla_vae.py:37-45 + data_utils.py:67-104
+//   Gaussian-NLL / MSE reconstruction     fwd / bwd     decoder.py:37-53     + data_utils.py:67-104
+//   stand-alone length-masked reduction   fwd / bwd     data_utils.py:67-104
+//   Philox eps materialisation                              (replaces torch.randn_like, vanilla_vae.py:39)
+//
+// All of them are HBM-streaming kernels: 16-byte vector loads/stores, one pass
+// over the data, warp-shuffle -> CTA -> per-CTA partial -> fixed-order final sum
+// by the last CTA (deterministic, no float atomics).  Roofline: HBM; algorithmic
+// bytes per frame are in DESIGN.md section "Kernels".
+#include "common.cuh"
+#include "philox.cuh"
+
+namespace mlvae {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr float kLog2Pi_f32 = 1.8378770351409912f;   // float32(log(float32(2*pi))), decoder.py:42
+constexpr float kReconEps = 1e-5f;                    // decoder.py:41
+
+template <typename T> __device__ __forceinline__ float fast_exp(float x);
+template <> __device__ __forceinline__ float fast_exp<float>(float x) { return expf(x); }
+template <> __device__ __forceinline__ float fast_exp<__nv_bfloat16>(float x) { return __expf(x); }
+
+// ---------------------------------------------------------------------------
+// Walks the (rows x C) matrix in units of VEC contiguous elements of one row.
+// Every thread keeps (row, column-vector, b, t) incrementally: no division in
+// the loop.  rows = B*T, row = b*T + t.
+// ---------------------------------------------------------------------------
+struct RowWalker {
+    int64_t vec, nvec;      // current / total vector index
+    int64_t step;           // threads in the grid
+    int vpr;                // vectors per row
+    int cv;                 // column vector of the current item
+    int b, t, T;
+    int step_rows, step_cv; // step / vpr, step % vpr
+    int srow_b, srow_t;     // step_rows / T, step_rows % T
+
+    __device__ __forceinline__ RowWalker(int64_t rows, int vpr_, int T_) {
+        vpr = vpr_; T = T_;
+        nvec = rows * vpr;
+        step = (int64_t)gridDim.x * blockDim.x;
+        vec = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        const int64_t row = vec / vpr;
+        cv = (int)(vec - row * vpr);
+        b = (int)(row / T);
+        t = (int)(row - (int64_t)b * T);
+        step_rows = (int)(step / vpr);
+        step_cv = (int)(step - (int64_t)step_rows * vpr);
+        srow_b = step_rows / T;
+        srow_t = step_rows - srow_b * T;
+    }
+    __device__ __forceinline__ bool valid() const { return vec < nvec; }
+    __device__ __forceinline__ void next() {
+        vec += step;
+        cv += step_cv;
+        int carry = 0;
+        if (cv >= vpr) { cv -= vpr; carry = 1; }
+        b += srow_b;
+        t += srow_t + carry;
+        if (t >= T) { t -= T; ++b; }
+        if (t >= T) { t -= T; ++b; }
+    }
+};
+
+// Final, deterministic reduction: the last CTA to arrive sums the per-CTA
+// partials in index order (double accumulation) and writes {mean, sum, count}.
+__device__ __forceinline__ bool last_cta_arrives(ReduceScratch *s) {
+    __shared__ bool s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(&s->ticket, 1u);
+        s_last = (prev == gridDim.x - 1);
+    }
+    __syncthreads();
+    return s_last;
+}
+
+__device__ __forceinline__ double ordered_sum(const float *p, int n) {
+    // warp 0 only: lane-strided double sums, then a fixed butterfly
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += 32) acc += (double)__ldcg(p + i);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    return acc;
+}
+
+__device__ __forceinline__ int64_t total_valid_frames(const float *lens, int B, int T) {
+    // warp 0 only
+    int64_t n = 0;
+    for (int b = threadIdx.x; b < B; b += 32) n += valid_frames(__ldg(lens + b), T);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+    return n;
+}
+
+__device__ __forceinline__ void finish_masked_mean(float local, ReduceScratch *s, const float *lens, int B,
+                                                   int T, int C, float *out) {
+    const float bs = block_sum(local);
+    if (threadIdx.x == 0) s->partial[blockIdx.x] = bs;
+    if (last_cta_arrives(s)) {
+        if (threadIdx.x < 32) {
+            const double tot = ordered_sum(s->partial, gridDim.x);
+            const int64_t frames = total_valid_frames(lens, B, T);
+            if (threadIdx.x == 0) {
+                const float cnt = (float)(frames * (int64_t)C);
+                out[0] = (float)tot / cnt;       // 0/0 -> NaN exactly like sum/sum(mask) in the reference
+                out[1] = (float)tot;
+                out[2] = cnt;
+                s->ticket = 0;                   // leave the scratch ready for the next launch
+            }
+        }
+    }
+}
+
+// 1 / (count*C) * upstream scalar, or 0 when no reduced-loss gradient flows.
+__device__ __forceinline__ float mean_grad_scale(const float *g_mean, const float *lens, int B, int T, int C) {
+    __shared__ float s_scale;
+    if (g_mean == nullptr) return 0.f;
+    if (threadIdx.x < 32) {
+        const int64_t frames = total_valid_frames(lens, B, T);
+        if (threadIdx.x == 0) s_scale = __ldg(g_mean) / (float)(frames * (int64_t)C);
+    }
+    __syncthreads();
+    return s_scale;
+}
+
+// ------------------------------------------------------------- Philox ------
+__global__ void __launch_bounds__(kThreads) philox_u32_kernel(uint64_t seed, uint64_t offset, int64_t n, uint32_t *out) {
+    const PhiloxKey key(seed);
+    const int64_t nblk = (n + 3) / 4;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nblk; q += (int64_t)gridDim.x * blockDim.x) {
+        const uint4 r = philox4x32_10(make_uint4((uint32_t)q, (uint32_t)((uint64_t)q >> 32), (uint32_t)offset, (uint32_t)(offset >> 32)), key);
+        const uint32_t v[4] = {r.x, r.y, r.z, r.w};
+        for (int k = 0; k < 4; ++k)
+            if (4 * q + k < n) out[4 * q + k] = v[k];
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) philox_normal_kernel(uint64_t seed, uint64_t offset, int64_t n, T *out) {
+    const PhiloxKey key(seed);
+    const int64_t nblk = (n + 3) / 4;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nblk; q += (int64_t)gridDim.x * blockDim.x) {
+        float v[4];
+        philox_normal4((uint64_t)q, offset, key, v);
+        for (int k = 0; k < 4; ++k)
+            if (4 * q + k < n) out[4 * q + k] = from_f32<T>(v[k]);
+    }
+}
+
+// eps for VEC (= 1, 4 or 8) consecutive stream elements starting at element e0.
+template <int VEC>
+__device__ __forceinline__ void stream_eps(int64_t e0, uint64_t offset, const PhiloxKey &key, float *eps) {
+    if constexpr (VEC == 1) {
+        float v[4];
+        philox_normal4((uint64_t)e0 >> 2, offset, key, v);
+        eps[0] = v[e0 & 3];
+    } else {
+#pragma unroll
+        for (int j = 0; j < VEC / 4; ++j) philox_normal4(((uint64_t)e0 >> 2) + j, offset, key, eps + 4 * j);
+    }
+}
+
+template <typename T, int VEC> struct Chunk {   // VEC == Vec<T>::N (vector path) or 1 (scalar path)
+    float v[VEC];
+    __device__ __forceinline__ void load(const T *p) {
+        if constexpr (VEC == 1) v[0] = to_f32<T>(__ldg(p));
+        else { Vec<T> x; x.load_stream(p);
+#pragma unroll
+               for (int i = 0; i < VEC; ++i) v[i] = x.v[i]; }
+    }
+    __device__ __forceinline__ void store(T *p) const {
+        if constexpr (VEC == 1) p[0] = from_f32<T>(v[0]);
+        else { Vec<T> x;
+#pragma unroll
+               for (int i = 0; i < VEC; ++i) x.v[i] = v[i];
+               x.store(p); }
+    }
+    __device__ __forceinline__ void zero() {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) v[i] = 0.f;
+    }
+};
+
+// ------------------------------------------------ reparameterise + KL ------
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kThreads)
+reparam_kl_fwd_kernel(const T *__restrict__ mu, const T *__restrict__ logvar, const T *__restrict__ eps,
+                      uint64_t seed, uint64_t offset, const float *__restrict__ lens, int B, int Tn, int L,
+                      T *__restrict__ z, T *__restrict__ kl_elem, float *__restrict__ kl_out, ReduceScratch *scratch) {
+    const PhiloxKey key(seed);
+    float acc = 0.f;
+    for (RowWalker w((int64_t)B * Tn, L / VEC, Tn); w.valid(); w.next()) {
+        const int64_t e0 = w.vec * VEC;
+        Chunk<T, VEC> m, lv, ep, zz, kk;
+        m.load(mu + e0);
+        lv.load(logvar + e0);
+        if (eps) ep.load(eps + e0);
+        else stream_eps<VEC>(e0, offset, key, ep.v);
+        float maskf = 1.f;
+        if (kl_out) maskf = ((float)w.t < mask_threshold(__ldg(lens + w.b), Tn)) ? 1.f : 0.f;
+        float part = 0.f;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            const float sd = fast_exp<T>(0.5f * lv.v[i]);
+            zz.v[i] = fmaf(ep.v[i], sd, m.v[i]);
+            const float k = -0.5f * (1.f + lv.v[i] - m.v[i] * m.v[i] - sd * sd);
+            kk.v[i] = k;
+            part += k * maskf;      // multiply, not select: inf*0 = NaN like loss*mask in the reference
+        }
+        acc += part;
+        zz.store(z + e0);
+        if (kl_elem) kk.store(kl_elem + e0);
+    }
+    if (kl_out) finish_masked_mean(acc, scratch, lens, B, Tn, L, kl_out);
+}
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kThreads)
+reparam_kl_bwd_kernel(const T *__restrict__ mu, const T *__restrict__ logvar, const T *__restrict__ eps,
+                      uint64_t seed, uint64_t offset, const T *__restrict__ grad_z,
+                      const T *__restrict__ grad_kl_elem, const float *__restrict__ grad_kl_mean,
+                      const float *__restrict__ lens, int B, int Tn, int L,
+                      T *__restrict__ grad_mu, T *__restrict__ grad_logvar) {
+    const PhiloxKey key(seed);
+    const float gscale = mean_grad_scale(grad_kl_mean, lens, B, Tn, L);
+    for (RowWalker w((int64_t)B * Tn, L / VEC, Tn); w.valid(); w.next()) {
+        const int64_t e0 = w.vec * VEC;
+        Chunk<T, VEC> m, lv, ep, gz, ge, gm, gl;
+        m.load(mu + e0);
+        lv.load(logvar + e0);
+        if (grad_z) gz.load(grad_z + e0); else gz.zero();
+        if (grad_kl_elem) ge.load(grad_kl_elem + e0); else ge.zero();
+        if (eps) ep.load(eps + e0);
+        else stream_eps<VEC>(e0, offset, key, ep.v);
+        float gm_row = 0.f;
+        if (grad_kl_mean) gm_row = gscale * (((float)w.t < mask_threshold(__ldg(lens + w.b), Tn)) ? 1.f : 0.f);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            const float sd = fast_exp<T>(0.5f * lv.v[i]);
+            const float g = ge.v[i] + gm_row;
+            gm.v[i] = fmaf(g, m.v[i], gz.v[i]);
+            gl.v[i] = fmaf(gz.v[i] * 0.5f * sd, ep.v[i], g * 0.5f * (sd * sd - 1.f));
+        }
+        gm.store(grad_mu + e0);
+        gl.store(grad_logvar + e0);
+    }
+}
+
+// ------------------------------------------------ reconstruction loss ------
+template <typename T, int VEC, bool kMse>
+__global__ void __launch_bounds__(kThreads)
+recon_fwd_kernel(const T *__restrict__ mean, const T *__restrict__ logvar, const T *__restrict__ target,
+                 const float *__restrict__ lens, int B, int Tn, int D, T *__restrict__ elem,
+                 float *__restrict__ out, ReduceScratch *scratch) {
+    float acc = 0.f;
+    for (RowWalker w((int64_t)B * Tn, D / VEC, Tn); w.valid(); w.next()) {
+        const int64_t e0 = w.vec * VEC;
+        Chunk<T, VEC> m, lv, tg, ll;
+        m.load(mean + e0);
+        tg.load(target + e0);
+        if constexpr (!kMse) lv.load(logvar + e0);
+        float maskf = 1.f;
+        if (out) maskf = ((float)w.t < mask_threshold(__ldg(lens + w.b), Tn)) ? 1.f : 0.f;
+        float part = 0.f;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            const float d = tg.v[i] - m.v[i];
+            float l;
+            if constexpr (kMse) l = d * d;
+            else l = 0.5f * (kLog2Pi_f32 + lv.v[i] + d * d / (fast_exp<T>(lv.v[i]) + kReconEps));
+            ll.v[i] = l;
+            part += l * maskf;
+        }
+        acc += part;
+        if (elem) ll.store(elem + e0);
+    }
+    if (out) finish_masked_mean(acc, scratch, lens, B, Tn, D, out);
+}
+
+template <typename T, int VEC, bool kMse>
+__global__ void __launch_bounds__(kThreads)
+recon_bwd_kernel(const T *__restrict__ mean, const T *__restrict__ logvar, const T *__restrict__ target,
+                 const T *__restrict__ grad_elem, const float *__restrict__ grad_mean_scalar,
+                 const float *__restrict__ lens, int B, int Tn, int D,
+                 T *__restrict__ grad_mean, T *__restrict__ grad_logvar, T *__restrict__ grad_target) {
+    const float gscale = mean_grad_scale(grad_mean_scalar, lens, B, Tn, D);
+    for (RowWalker w((int64_t)B * Tn, D / VEC, Tn); w.valid(); w.next()) {
+        const int64_t e0 = w.vec * VEC;
+        Chunk<T, VEC> m, lv, tg, ge, gm, gl, gt;
+        m.load(mean + e0);
+        tg.load(target + e0);
+        if constexpr (!kMse) lv.load(logvar + e0);
+        if (grad_elem) ge.load(grad_elem + e0); else ge.zero();
+        float gm_row = 0.f;
+        if (grad_mean_scalar) gm_row = gscale * (((float)w.t < mask_threshold(__ldg(lens + w.b), Tn)) ? 1.f : 0.f);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            const float g = ge.v[i] + gm_row;
+            const float d = tg.v[i] - m.v[i];
+            if constexpr (kMse) {
+                gt.v[i] = 2.f * d * g;
+                gm.v[i] = -gt.v[i];
+            } else {
+                const float e = fast_exp<T>(lv.v[i]);
+                const float inv = 1.f / (e + kReconEps);
+                gt.v[i] = g * d * inv;                       // d/dtarget = (t-m)/(e+eps)
+                gm.v[i] = -gt.v[i];
+                gl.v[i] = g * 0.5f * (1.f - d * d * e * inv * inv);
+            }
+        }
+        gm.store(grad_mean + e0);
+        if constexpr (!kMse) gl.store(grad_logvar + e0);
+        if (grad_target) gt.store(grad_target + e0);
+    }
+}
+
+// ------------------------------------------ stand-alone masked reduction ----
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kThreads)
+masked_sum_kernel(const T *__restrict__ loss, const float *__restrict__ lens, int B, int Tn, int C, int reduction,
+                  float *__restrict__ out, ReduceScratch *scratch) {
+    float acc = 0.f;
+    for (RowWalker w((int64_t)B * Tn, C / VEC, Tn); w.valid(); w.next()) {
+        Chunk<T, VEC> x;
+        x.load(loss + w.vec * VEC);
+        const float maskf = ((float)w.t < mask_threshold(__ldg(lens + w.b), Tn)) ? 1.f : 0.f;
+        float part = 0.f;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) part += x.v[i] * maskf;
+        acc += part;
+    }
+    const float bs = block_sum(acc);
+    if (threadIdx.x == 0) scratch->partial[blockIdx.x] = bs;
+    if (last_cta_arrives(scratch) && threadIdx.x < 32) {
+        const double tot = ordered_sum(scratch->partial, gridDim.x);
+        const int64_t frames = total_valid_frames(lens, B, Tn);
+        if (threadIdx.x == 0) {
+            const float denom = (reduction == MLVAE_RED_MEAN) ? (float)(frames * (int64_t)C) : (float)B;
+            out[0] = (float)tot / denom;
+            scratch->ticket = 0;
+        }
+    }
+}
+
+// 'batch' reduction: one CTA per utterance row (B is small; T*C per row is what is summed).
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+masked_rowmean_kernel(const T *__restrict__ loss, const float *__restrict__ lens, int Tn, int C, float *__restrict__ out) {
+    const int b = blockIdx.x;
+    const float thr = mask_threshold(__ldg(lens + b), Tn);
+    const T *row = loss + (int64_t)b * Tn * C;
+    float acc = 0.f;
+    for (int64_t i = threadIdx.x; i < (int64_t)Tn * C; i += blockDim.x) {
+        const int t = (int)(i / C);
+        acc += to_f32<T>(__ldg(row + i)) * (((float)t < thr) ? 1.f : 0.f);
+    }
+    const float s = block_sum(acc);
+    if (threadIdx.x == 0) out[b] = s / (float)((int64_t)valid_frames(__ldg(lens + b), Tn) * C);
+}
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kThreads)
+masked_reduce_bwd_kernel(const float *__restrict__ grad_out, const float *__restrict__ lens, int B, int Tn, int C,
+                         int reduction, T *__restrict__ grad_loss) {
+    __shared__ float s_scale;
+    if (reduction != MLVAE_RED_BATCH) {
+        if (threadIdx.x < 32) {
+            const int64_t frames = total_valid_frames(lens, B, Tn);
+            if (threadIdx.x == 0)
+                s_scale = __ldg(grad_out) / ((reduction == MLVAE_RED_MEAN) ? (float)(frames * (int64_t)C) : (float)B);
+        }
+        __syncthreads();
+    }
+    for (RowWalker w((int64_t)B * Tn, C / VEC, Tn); w.valid(); w.next()) {
+        const float len_b = __ldg(lens + w.b);
+        float g = ((float)w.t < mask_threshold(len_b, Tn)) ? 1.f : 0.f;
+        if (reduction == MLVAE_RED_BATCH) g *= __ldg(grad_out + w.b) / (float)((int64_t)valid_frames(len_b, Tn) * C);
+        else g *= s_scale;
+        Chunk<T, VEC> x;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) x.v[i] = g;
+        x.store(grad_loss + w.vec * VEC);
+    }
+}
+
+// ------------------------------------------------------------ launching ----
+inline int grid_for(int64_t nvec, int ctas_per_sm = 8) {
+    int64_t g = (nvec + kThreads - 1) / kThreads;
+    const int64_t cap = (int64_t)sm_count() * ctas_per_sm;
+    if (g > cap) g = cap;
+    if (g > kMaxPartials) g = kMaxPartials;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int check_btc(int B, int T, int C) {
+    MLVAE_REQUIRE(B > 0 && T > 0 && C > 0, MLVAE_ERR_INVALID_ARG, "B, T, C must be positive (got %d, %d, %d)", B, T, C);
+    MLVAE_REQUIRE((int64_t)B * T < (1LL << 31), MLVAE_ERR_UNSUPPORTED, "B*T must be < 2^31");
+    return MLVAE_OK;
+}
+
+}  // namespace
+}  // namespace mlvae
+
+using namespace mlvae;
+
+// Dispatch helper: vector path when the row length and every pointer allow 16-byte access.
+#define MLVAE_DISPATCH(DT, C, ALIGNED, ...)                                                    \
+    do {                                                                                       \
+        if ((DT) == MLVAE_F32) {                                                               \
+            using T = float;                                                                   \
+            if ((ALIGNED) && (C) % 4 == 0) { constexpr int VEC = 4; __VA_ARGS__; }                    \
+            else { constexpr int VEC = 1; __VA_ARGS__; }                                              \
+        } else if ((DT) == MLVAE_BF16) {                                                       \
+            using T = __nv_bfloat16;                                                           \
+            if ((ALIGNED) && (C) % 8 == 0) { constexpr int VEC = 8; __VA_ARGS__; }                    \
+            else { constexpr int VEC = 1; __VA_ARGS__; }                                              \
+        } else                                                                                 \
+            return fail(MLVAE_ERR_INVALID_ARG, "unknown dtype %d", (int)(DT));                 \
+    } while (0)
+
+extern "C" {
+
+int mlvae_abi_version(void) { return MLVAE_ABI_VERSION; }
+const char *mlvae_last_error(void) { return err_buf(); }
+
+int mlvae_device_info(int *sms, int *cc) {
+    int dev = 0, n = 0, maj = 0, min = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return fail(MLVAE_ERR_NO_DEVICE, "no CUDA device");
+    MLVAE_CHECK_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    MLVAE_CHECK_CUDA(cudaDeviceGetAttribute(&maj, cudaDevAttrComputeCapabilityMajor, dev));
+    MLVAE_CHECK_CUDA(cudaDeviceGetAttribute(&min, cudaDevAttrComputeCapabilityMinor, dev));
+    if (sms) *sms = n;
+    if (cc) *cc = maj * 10 + min;
+    return MLVAE_OK;
+}
+
+size_t mlvae_reduce_scratch_bytes(void) { return sizeof(ReduceScratch); }
+
+int mlvae_philox_u32(uint64_t seed, uint64_t offset, int64_t n, uint32_t *d_out, void *stream) {
+    MLVAE_REQUIRE(d_out && n >= 0, MLVAE_ERR_INVALID_ARG, "philox_u32: bad arguments");
+    if (n == 0) return MLVAE_OK;
+    philox_u32_kernel<<<grid_for((n + 3) / 4), kThreads, 0, (cudaStream_t)stream>>>(seed, offset, n, d_out);
+    MLVAE_CHECK_CUDA(cudaGetLastError());
+    return MLVAE_OK;
+}
+
+int mlvae_philox_normal(uint64_t seed, uint64_t offset, int64_t n, void *d_out, int dtype, void *stream) {
+    MLVAE_REQUIRE(d_out && n >= 0, MLVAE_ERR_INVALID_ARG, "philox_normal: bad arguments");
+    if (n == 0) return MLVAE_OK;
+    const int g = grid_for((n + 3) / 4);
+    if (dtype == MLVAE_F32) philox_normal_kernel<float><<<g, kThreads, 0, (cudaStream_t)stream>>>(seed, offset, n, (float *)d_out);
+    else if (dtype == MLVAE_BF16) philox_normal_kernel<__nv_bfloat16><<<g, kThreads, 0, (cudaStream_t)stream>>>(seed, offset, n, (__nv_bfloat16 *)d_out);
+    else return fail(MLVAE_ERR_INVALID_ARG, "unknown dtype %d", dtype);
+    MLVAE_CHECK_CUDA(cudaGetLastError());
+    return MLVAE_OK;
+}
+
+int mlvae_reparam_kl_fwd(const void *d_mu, const void *d_logvar, const void *d_eps, uint64_t seed, uint64_t offset,
+                         const float *d_lens, int B, int T_, int L, int dtype, void *d_z, void *d_kl_elem,
+                         float *d_kl_out, void *d_scratch, void *stream) {
+    if (int rc = check_btc(B, T_, L)) return rc;
+    MLVAE_REQUIRE(d_mu && d_logvar && d_z, MLVAE_ERR_INVALID_ARG, "reparam_kl_fwd: mu, logvar and z are required");
+    MLVAE_REQUIRE(!d_kl_out || (d_lens && d_scratch), MLVAE_ERR_INVALID_ARG, "reparam_kl_fwd: reduced KL needs lens and scratch");
+    const bool al = aligned16(d_mu) && aligned16(d_logvar) && aligned16(d_z) && aligned16(d_eps) && aligned16(d_kl_elem);
+    MLVAE_DISPATCH(dtype, L, al, {
+        const int64_t nvec = (int64_t)B * T_ * (L / VEC);
+        reparam_kl_fwd_kernel<T, VEC><<<grid_for(nvec), kThreads, 0, (cudaStream_t)stream>>>(
+            (const T *)d_mu, (const T *)d_logvar, (const T *)d_eps, seed, offset, d_lens, B, T_, L, (T *)d_z,
+            (T *)d_kl_elem, d_kl_out, (ReduceScratch *)d_scratch);
+    });
+    MLVAE_CHECK_CUDA(cudaGetLastError());
+    return MLVAE_OK;
+}
+
+int mlvae_reparam_kl_bwd(const void *d_mu, const void *d_logvar, const void *d_eps, uint64_t seed, uint64_t offset,
+                         const void *d_grad_z, const void *d_grad_kl_elem, const float *d_grad_kl_mean,
+                         const float *d_lens, int B, int T_, int L, int dtype, void *d_grad_mu, void *d_grad_logvar,
+                         void *stream) {
+    if (int rc = check_btc(B, T_, L)) return rc;
+    MLVAE_REQUIRE(d_mu && d_logvar && d_grad_mu && d_grad_logvar, MLVAE_ERR_INVALID_ARG, "reparam_kl_bwd: missing buffers");
+    MLVAE_REQUIRE(!d_grad_kl_mean || d_lens, MLVAE_ERR_INVALID_ARG, "reparam_kl_bwd: reduced-KL gradient needs lens");
+    const bool al = aligned16(d_mu) && aligned16(d_logvar) && aligned16(d_eps) && aligned16(d_grad_z) &&
+                    aligned16(d_grad_kl_elem) && aligned16(d_grad_mu) && aligned16(d_grad_logvar);
+    MLVAE_DISPATCH(dtype, L, al, {
+        const int64_t nvec = (int64_t)B * T_ * (L / VEC);
+        reparam_kl_bwd_kernel<T, VEC><<<grid_for(nvec), kThreads, 0, (cudaStream_t)stream>>>(
+            (const T *)d_mu, (const T *)d_logvar, (const T *)d_eps, seed, offset, (const T *)d_grad_z,
+            (const T *)d_grad_kl_elem, d_grad_kl_mean, d_lens, B, T_, L, (T *)d_grad_mu, (T *)d_grad_logvar);
+    });
+    MLVAE_CHECK_CUDA(cudaGetLastError());
+    return MLVAE_OK;
+}
+
+int mlvae_recon_fwd(const void *d_mean, const void *d_logvar, const void *d_target, const float *d_lens, int B, int T_,
+                    int D, int dtype, int loss_type, void *d_elem, float *d_out, void *d_scratch, void *stream) {
+    if (int rc = check_btc(B, T_, D)) return rc;
+    MLVAE_REQUIRE(loss_type == MLVAE_RECON_LIKELIHOOD || loss_type == MLVAE_RECON_MSE, MLVAE_ERR_INVALID_ARG,
+                  "Invalid loss type: %d", loss_type);
+    const bool mse = loss_type == MLVAE_RECON_MSE;
+    MLVAE_REQUIRE(d_mean && d_target && (mse || d_logvar), MLVAE_ERR_INVALID_ARG, "recon_fwd: missing inputs");
+    MLVAE_REQUIRE(d_elem || d_out, MLVAE_ERR_INVALID_ARG, "recon_fwd: nothing to write");
+    MLVAE_REQUIRE(!d_out || (d_lens && d_scratch), MLVAE_ERR_INVALID_ARG, "recon_fwd: reduced loss needs lens and scratch");
+    const bool al = aligned16(d_mean) && aligned16(d_logvar) && aligned16(d_target) && aligned16(d_elem);
+    MLVAE_DISPATCH(dtype, D, al, {
+        const int64_t nvec = (int64_t)B * T_ * (D / VEC);
+        const int g = grid_for(nvec);
+        if (mse)
+            recon_fwd_kernel<T, VEC, true><<<g, kThreads, 0, (cudaStream_t)stream>>>(
+                (const T *)d_mean, (const T *)d_logvar, (const T *)d_target, d_lens, B, T_, D, (T *)d_elem, d_out,
+                (ReduceScratch *)d_scratch);
+        else
+            recon_fwd_kernel<T, VEC, false><<<g, kThreads, 0, (cudaStream_t)stream>>>(
+                (const T *)d_mean, (const T *)d_logvar, (const T *)d_target, d_lens, B, T_, D, (T *)d_elem, d_out,
+                (ReduceScratch *)d_scratch);
+    });
+    MLVAE_CHECK_CUDA(cudaGetLastError());
+    return MLVAE_OK;
+}
+
+int mlvae_recon_bwd(const void *d_mean, const void *d_logvar, const void *d_target, const void *d_grad_elem,
+                    const float *d_grad_mean_scalar, const float *d_lens, int B, int T_, int D, int dtype,
+                    int loss_type, void *d_grad_mean, void *d_grad_logvar, void *d_grad_target, void *stream) {
+    if (int rc = check_btc(B, T_, D)) return rc;
+    MLVAE_REQUIRE(loss_type == MLVAE_RECON_LIKELIHOOD || loss_type == MLVAE_RECON_MSE, MLVAE_ERR_INVALID_ARG,
+                  "Invalid loss type: %d", loss_type);
+    const bool mse = loss_type == MLVAE_RECON_MSE;
+    MLVAE_REQUIRE(d_mean && d_target && d_grad_mean && (mse || (d_logvar && d_grad_logvar)), MLVAE_ERR_INVALID_ARG,
+                  "recon_bwd: missing buffers");
+    MLVAE_REQUIRE(!d_grad_mean_scalar || d_lens, MLVAE_ERR_INVALID_ARG, "recon_bwd: reduced-loss gradient needs lens");
+    const bool al = aligned16(d_mean) && aligned16(d_logvar) && aligned16(d_target) && aligned16(d_grad_elem) &&
+                    aligned16(d_grad_mean) && aligned16(d_grad_logvar) && aligned16(d_grad_target);
+    MLVAE_DISPATCH(dtype, D, al, {
+        const int64_t nvec = (int64_t)B * T_ * (D / VEC);
+        const int g = grid_for(nvec);
+        if (mse)
+            recon_bwd_kernel<T, VEC, true><<<g, kThreads, 0, (cudaStream_t)stream>>>(
+                (const T *)d_mean, (const T *)d_logvar, (const T *)d_target, (const T *)d_grad_elem, d_grad_mean_scalar,
+                d_lens, B, T_, D, (T *)d_grad_mean, (T *)d_grad_logvar, (T *)d_grad_target);
+        else
+            recon_bwd_kernel<T, VEC, false><<<g, kThreads, 0, (cudaStream_t)stream>>>(
+                (const T *)d_mean, (const T *)d_logvar, (const T *)d_target, (const T *)d_grad_elem, d_grad_mean_scalar,
+                d_lens, B, T_, D, (T *)d_grad_mean, (T *)d_grad_logvar, (T *)d_grad_target);
+    });
+    MLVAE_CHECK_CUDA(cudaGetLastError());
+    return MLVAE_OK;
+}
+
+int mlvae_masked_reduce_fwd(const void *d_loss, const float *d_lens, int B, int T_, int C, int dtype, int reduction,
+                            float *d_out, void *d_scratch, void *stream) {
+    if (int rc = check_btc(B, T_, C)) return rc;
+    MLVAE_REQUIRE(d_loss && d_lens && d_out, MLVAE_ERR_INVALID_ARG, "masked_reduce_fwd: missing buffers");
+    MLVAE_REQUIRE(reduction >= MLVAE_RED_MEAN && reduction <= MLVAE_RED_BATCH, MLVAE_ERR_INVALID_ARG, "bad reduction %d", reduction);
+    if (reduction == MLVAE_RED_BATCH) {
+        if (dtype == MLVAE_F32) masked_rowmean_kernel<float><<<B, kThreads, 0, (cudaStream_t)stream>>>((const float *)d_loss, d_lens, T_, C, d_out);
+        else if (dtype == MLVAE_BF16) masked_rowmean_kernel<__nv_bfloat16><<<B, kThreads, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)d_loss, d_lens, T_, C, d_out);
+        else return fail(MLVAE_ERR_INVALID_ARG, "unknown dtype %d", dtype);
+    } else {
+        MLVAE_REQUIRE(d_scratch, MLVAE_ERR_INVALID_ARG, "masked_reduce_fwd: scratch required");
+        MLVAE_DISPATCH(dtype, C, aligned16(d_loss), {
+            const int64_t nvec = (int64_t)B * T_ * (C / VEC);
+            masked_sum_kernel<T, VEC><<<grid_for(nvec), kThreads, 0, (cudaStream_t)stream>>>(
+                (const T *)d_loss, d_lens, B, T_, C, reduction, d_out, (ReduceScratch *)d_scratch);
+        });
+    }
+    MLVAE_CHECK_CUDA(cudaGetLastError());
+    return MLVAE_OK;
+}
+
+int mlvae_masked_reduce_bwd(const float *d_grad_out, const float *d_lens, int B, int T_, int C, int dtype, int reduction,
+                            void *d_grad_loss, void *stream) {
+    if (int rc = check_btc(B, T_, C)) return rc;
+    MLVAE_REQUIRE(d_grad_out && d_lens && d_grad_loss, MLVAE_ERR_INVALID_ARG, "masked_reduce_bwd: missing buffers");
+    MLVAE_REQUIRE(reduction >= MLVAE_RED_MEAN && reduction <= MLVAE_RED_BATCH, MLVAE_ERR_INVALID_ARG, "bad reduction %d", reduction);
+    MLVAE_DISPATCH(dtype, C, aligned16(d_grad_loss), {
+        const int64_t nvec = (int64_t)B * T_ * (C / VEC);
+        masked_reduce_bwd_kernel<T, VEC><<<grid_for(nvec), kThreads, 0, (cudaStream_t)stream>>>(
+            d_grad_out, d_lens, B, T_, C, reduction, (T *)d_grad_loss);
+    });
+    MLVAE_CHECK_CUDA(cudaGetLastError());
+    return MLVAE_OK;
+}
+
+}  // extern "C"

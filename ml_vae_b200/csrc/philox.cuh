@@ -1,0 +1,51 @@
+// Philox4x32-10 and the eps stream of the reparameterisation kernels.
+// Host restatement: oracle/philox_ref.py (the stream definition lives there).
+#pragma once
+#include <stdint.h>
+
+namespace mlvae {
+
+struct PhiloxKey {
+    uint32_t k0[10], k1[10];   // per-round keys, precomputed once per thread
+    __device__ __forceinline__ explicit PhiloxKey(uint64_t seed) {
+        uint32_t a = (uint32_t)seed, b = (uint32_t)(seed >> 32);
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+            k0[r] = a; k1[r] = b;
+            a += 0x9E3779B9u; b += 0xBB67AE85u;
+        }
+    }
+};
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, const PhiloxKey &key) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ key.k0[r], lo1, hi0 ^ c.w ^ key.k1[r], lo0);
+    }
+    return c;
+}
+
+// Box-Muller on one (a, b) pair of uint32:
+//   u1 = fl32(fl32(a) + 1) * 2^-32 in (0, 1],   theta = fl32(int32(b)) * (pi * 2^-31) in [-pi, pi)
+//   n0 = r cos(theta), n1 = r sin(theta), r = sqrt(-2 ln u1)
+// MUFU-based (lg2 / sqrt / sin / cos approx): abs error < 2e-6, see tests/test_philox.py.
+__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float &n0, float &n1) {
+    const float u1 = (__uint2float_rn(a) + 1.0f) * 2.3283064365386963e-10f;
+    const float th = __int2float_rn((int)b) * 1.4629180792671596e-9f;
+    const float r = sqrtf(-2.0f * __logf(u1));
+    float s, c;
+    __sincosf(th, &s, &c);
+    n0 = r * c;
+    n1 = r * s;
+}
+
+// 4 consecutive normals of the stream: elements [4q, 4q+4).
+__device__ __forceinline__ void philox_normal4(uint64_t q, uint64_t offset, const PhiloxKey &key, float out[4]) {
+    const uint4 r = philox4x32_10(make_uint4((uint32_t)q, (uint32_t)(q >> 32), (uint32_t)offset, (uint32_t)(offset >> 32)), key);
+    box_muller(r.x, r.y, out[0], out[1]);
+    box_muller(r.z, r.w, out[2], out[3]);
+}
+
+}  // namespace mlvae

@@ -1,0 +1,5 @@
+"""Drop-in counterparts of the reference's src/modules/{fc_block,vanilla_vae,decoder}.py
+with identical constructor kwargs, forward() dict contracts and state_dict keys."""
+from .fc_block import FCBlock  # noqa: F401
+from .vanilla_vae import VanillaVAE  # noqa: F401
+from .decoder import Decoder  # noqa: F401

@@ -1,0 +1,70 @@
+"""Drop-in for the reference's modules/decoder.py:10-53 (Decoder).
+
+Same constructor kwargs (input_size, rnn_hidden_size, rnn_num_layers, rnn_dropout,
+fc_sizes, loss_type='likelihood'), checkpoint keys (rnn.weight_ih_l0[_reverse]...,
+mean_fc.blocks.{0,2,4}.*, log_var_fc.blocks.{0,2,4}.*) and forward() dict
+{'mean', 'log_var', 'losses': {'recon_loss': unreduced (B, T, D)}}; an unknown
+loss_type raises ValueError exactly like decoder.py:51.
+
+The reconstruction loss (and, with ``lens=``, its length-masked mean) is one fused
+kernel; the dead Normal.log_prob of decoder.py:45-47 is not computed.  The biLSTM is
+cuDNN through torch (SURVEY.md section 8f-1 ranks its replacement first among the "next" rows).
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from .. import ops
+from ..dense import linear_chain
+from ._params import attach, torch_default_linear, torch_default_lstm
+
+
+class Decoder(nn.Module):
+    def __init__(self, input_size, rnn_hidden_size, rnn_num_layers, rnn_dropout, fc_sizes, loss_type="likelihood",
+                 materialize_loss: bool = True):
+        super().__init__()
+        self.input_size = int(input_size)
+        self.hidden = int(rnn_hidden_size)
+        self.num_layers = int(rnn_num_layers)
+        self.rnn_dropout = float(rnn_dropout)
+        self.fc_sizes = [int(s) for s in fc_sizes]
+        self.loss_type = loss_type
+        self.materialize_loss = materialize_loss
+        self._rnn_names = []
+        for name, p in torch_default_lstm(self.input_size, self.hidden, self.num_layers):
+            attach(self, f"rnn.{name}", p)
+            self._rnn_names.append(name)
+        for head in ("mean_fc", "log_var_fc"):
+            for i in range(len(self.fc_sizes) - 1):
+                w, b = torch_default_linear(self.fc_sizes[i], self.fc_sizes[i + 1])
+                attach(self, f"{head}.blocks.{2 * i}.weight", w)
+                attach(self, f"{head}.blocks.{2 * i}.bias", b)
+
+    def _head(self, name):
+        blocks = getattr(self, name).blocks._modules
+        n = len(self.fc_sizes) - 1
+        return [blocks[str(2 * i)].weight for i in range(n)], [blocks[str(2 * i)].bias for i in range(n)]
+
+    def run_rnn(self, x):
+        """decoder.py:14-15,22: 2-layer bidirectional LSTM, batch_first, inter-layer dropout."""
+        flat = [getattr(self.rnn, n).to(x.dtype) for n in self._rnn_names]
+        z = x.new_zeros(2 * self.num_layers, x.shape[0], self.hidden)
+        out, _, _ = torch._VF.lstm(x, (z, z), flat, True, self.num_layers, self.rnn_dropout, self.training, True, True)
+        return out
+
+    def forward(self, sampled_h, target_feats, lens=None):
+        if self.loss_type not in ("likelihood", "mse"):
+            raise ValueError(f"Invalid loss type: {self.loss_type}")
+        rnn_out = self.run_rnn(sampled_h)
+        mean = linear_chain(rnn_out, *self._head("mean_fc"))
+        log_var = linear_chain(rnn_out, *self._head("log_var_fc"))
+        elem, red = ops.recon_loss(mean, log_var, target_feats, lens=lens, loss_type=self.loss_type,
+                                   want_elem=self.materialize_loss, want_mean=lens is not None)
+        out = {"mean": mean, "log_var": log_var, "losses": {"recon_loss": elem}}
+        if lens is not None:
+            out["recon_loss"] = red
+        return out
+
+    def compute_recon_loss(self, mean, log_var, target):
+        return ops.recon_loss(mean, log_var, target, loss_type=self.loss_type, want_elem=True, want_mean=False)[0]

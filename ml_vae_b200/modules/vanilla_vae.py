@@ -1,0 +1,81 @@
+"""Drop-in for the reference's modules/vanilla_vae.py:9-45 (VanillaVAE).
+
+Same constructor kwargs (fc_sizes, latent_size), same checkpoint keys
+(fc.0.blocks.{0,2}.*, mean_fc.*, log_var_fc.*) and the same forward() dict
+{'mean', 'log_var', 'sampled_h', 'loss'} with 'loss' the UNREDUCED (B, T, L) KL.
+
+Differences that are the point of this package:
+  * reparameterise + KL are one fused kernel (csrc/latent_loss.cu), forward and backward;
+  * eps is the counter-based Philox stream (seed, per-call offset) regenerated in the
+    backward instead of a stored torch.randn_like tensor; pass ``eps=`` to inject one
+    (parity tests), or call ``set_seed``;
+  * ``forward(feats, lens=...)`` additionally returns 'kld_loss', the length-masked mean
+    (apply_lens_to_loss) computed inside the same kernel without materialising 'loss'
+    when ``materialize_loss=False``.
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from .. import ops
+from ..dense import LEAKY_SLOPE, linear_chain
+from ._params import attach, torch_default_linear
+
+
+class VanillaVAE(nn.Module):
+    def __init__(self, fc_sizes, latent_size, seed: int = 123456, materialize_loss: bool = True):
+        super().__init__()
+        self.fc_sizes = [int(s) for s in fc_sizes]
+        self.latent_size = int(latent_size)
+        self.materialize_loss = materialize_loss
+        for i in range(len(self.fc_sizes) - 1):
+            w, b = torch_default_linear(self.fc_sizes[i], self.fc_sizes[i + 1])
+            attach(self, f"fc.0.blocks.{2 * i}.weight", w)
+            attach(self, f"fc.0.blocks.{2 * i}.bias", b)
+        for head in ("mean_fc", "log_var_fc"):
+            w, b = torch_default_linear(self.fc_sizes[-1], self.latent_size)
+            attach(self, f"{head}.weight", w)
+            attach(self, f"{head}.bias", b)
+        self.seed = int(seed)
+        self.calls = 0          # Philox offset: one fresh eps stream per forward
+
+    def set_seed(self, seed: int, calls: int = 0):
+        self.seed, self.calls = int(seed), int(calls)
+
+    def _trunk(self):
+        blocks = self.fc._modules["0"].blocks._modules
+        n = len(self.fc_sizes) - 1
+        return [blocks[str(2 * i)].weight for i in range(n)], [blocks[str(2 * i)].bias for i in range(n)]
+
+    def project(self, feats):
+        """feats (B, T, C) -> mean, log_var (B, T, L).  vanilla_vae.py:22-24."""
+        ws, bs = self._trunk()
+        h = linear_chain(feats, ws, bs, end_activation=True)
+        # both heads read h once: one GEMM against the stacked (2L, H) weight
+        w = torch.cat([self.mean_fc.weight, self.log_var_fc.weight], 0)
+        b = torch.cat([self.mean_fc.bias, self.log_var_fc.bias], 0)
+        ml = linear_chain(h, [w], [b])
+        mean, log_var = ml[..., : self.latent_size], ml[..., self.latent_size:]
+        return mean.contiguous(), log_var.contiguous()
+
+    def forward(self, feats, lens=None, eps=None):
+        mean, log_var = self.project(feats)
+        offset = self.calls
+        self.calls += 1
+        z, kl_elem, kl_mean = ops.reparam_kl(mean, log_var, lens=lens, eps=eps, seed=self.seed, offset=offset,
+                                             want_elem=self.materialize_loss, want_mean=lens is not None)
+        out = {"mean": mean, "log_var": log_var, "sampled_h": z, "loss": kl_elem}
+        if lens is not None:
+            out["kld_loss"] = kl_mean
+        return out
+
+    # kept for API parity with the reference class
+    def reparameterize(self, mean, log_var, eps=None):
+        offset = self.calls
+        self.calls += 1
+        return ops.reparam_kl(mean, log_var, eps=eps, seed=self.seed, offset=offset,
+                              want_elem=False, want_mean=False)[0]
+
+    def compute_kld_loss(self, mean, log_var):
+        return ops.reparam_kl(mean, log_var, eps=torch.zeros_like(mean), want_elem=True, want_mean=False)[1]

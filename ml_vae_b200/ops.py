@@ -1,0 +1,179 @@
+"""torch.autograd.Function wrappers over the C-ABI kernels (include/mlvae_b200.h).
+
+torch is used for device memory, streams and autograd plumbing only; all
+arithmetic of these ops happens in libmlvae_b200.so.  Reference semantics:
+  reparam_kl      modules/vanilla_vae.py:37-45  (+ utils/data_utils.py:67-104 when reduced)
+  recon_loss      modules/decoder.py:37-53      (+ utils/data_utils.py:67-104 when reduced)
+  masked_reduce   utils/data_utils.py:67-104
+  philox_normal   replaces torch.randn_like at modules/vanilla_vae.py:39
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib as L
+
+
+def _c(t):
+    return None if t is None else t.contiguous()
+
+
+def _btc(t: torch.Tensor):
+    if t.dim() < 2:
+        raise ValueError(f"expected (B, T, ...) tensor, got shape {tuple(t.shape)}")
+    b, tt = t.shape[0], t.shape[1]
+    c = 1
+    for s in t.shape[2:]:
+        c *= s
+    return b, tt, c
+
+
+def _lens(lens: torch.Tensor, like: torch.Tensor) -> torch.Tensor:
+    return lens.to(device=like.device, dtype=torch.float32).contiguous()
+
+
+def philox_normal(shape, seed: int, offset: int = 0, dtype=torch.float32, device="cuda") -> torch.Tensor:
+    """Materialise the eps stream the fused kernel would draw for (seed, offset)."""
+    out = torch.empty(shape, dtype=dtype, device=device)
+    L.require_cuda(out)
+    L.check(L.lib().mlvae_philox_normal(seed, offset, out.numel(), L.ptr(out), L.dtype_code(out), L.stream_ptr()),
+            "mlvae_philox_normal")
+    return out
+
+
+def philox_u32(n: int, seed: int, offset: int = 0, device="cuda") -> torch.Tensor:
+    out = torch.empty(n, dtype=torch.int32, device=device)
+    L.check(L.lib().mlvae_philox_u32(seed, offset, n, L.ptr(out), L.stream_ptr()), "mlvae_philox_u32")
+    return out
+
+
+class _ReparamKL(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mu, logvar, eps, lens, seed, offset, want_elem, want_mean):
+        L.require_cuda(mu, logvar, eps)
+        if mu.shape != logvar.shape or mu.dtype != logvar.dtype:
+            raise ValueError("mean and log_var must have the same shape and dtype")
+        mu, logvar, eps = _c(mu), _c(logvar), _c(eps)
+        if eps is not None and (eps.shape != mu.shape or eps.dtype != mu.dtype):
+            eps = eps.to(mu.dtype).reshape(mu.shape).contiguous()
+        B, T, C = _btc(mu)
+        z = torch.empty_like(mu)
+        kl_elem = torch.empty_like(mu) if want_elem else None
+        kl_out = torch.empty(3, dtype=torch.float32, device=mu.device) if want_mean else None
+        lens_f = _lens(lens, mu) if lens is not None else None
+        if want_mean and lens_f is None:
+            raise ValueError("reduced KL needs lens")
+        L.check(L.lib().mlvae_reparam_kl_fwd(
+            L.ptr(mu), L.ptr(logvar), L.ptr(eps), seed, offset, L.ptr(lens_f), B, T, C, L.dtype_code(mu),
+            L.ptr(z), L.ptr(kl_elem), L.ptr(kl_out), L.ptr(L.reduce_scratch(mu.device)) if want_mean else None,
+            L.stream_ptr()), "mlvae_reparam_kl_fwd")
+        ctx.save_for_backward(mu, logvar, eps, lens_f)
+        ctx.seed, ctx.offset = seed, offset
+        ctx.set_materialize_grads(False)
+        empty = mu.new_empty(0)
+        return z, (kl_elem if want_elem else empty), (kl_out[0] if want_mean else empty.float())
+
+    @staticmethod
+    def backward(ctx, gz, gelem, gmean):
+        mu, logvar, eps, lens_f = ctx.saved_tensors
+        B, T, C = _btc(mu)
+        gz = _c(gz)
+        gelem = _c(gelem) if gelem is not None and gelem.numel() else None
+        gmean = gmean.contiguous().float() if gmean is not None and gmean.numel() else None
+        if gz is not None and gz.dtype != mu.dtype:
+            gz = gz.to(mu.dtype)
+        gmu, glv = torch.empty_like(mu), torch.empty_like(mu)
+        L.check(L.lib().mlvae_reparam_kl_bwd(
+            L.ptr(mu), L.ptr(logvar), L.ptr(eps), ctx.seed, ctx.offset, L.ptr(gz), L.ptr(gelem), L.ptr(gmean),
+            L.ptr(lens_f), B, T, C, L.dtype_code(mu), L.ptr(gmu), L.ptr(glv), L.stream_ptr()), "mlvae_reparam_kl_bwd")
+        return gmu, glv, None, None, None, None, None, None
+
+
+def reparam_kl(mu, logvar, lens=None, eps=None, seed: int = 0, offset: int = 0,
+               want_elem: bool = False, want_mean: bool = True):
+    """-> (z, kl_elem | None, kl_mean | None).  eps=None draws Philox(seed, offset)."""
+    z, e, m = _ReparamKL.apply(mu, logvar, eps, lens, int(seed), int(offset), want_elem, want_mean)
+    return z, (e if want_elem else None), (m if want_mean else None)
+
+
+class _ReconLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mean, logvar, target, lens, loss_type, want_elem, want_mean):
+        if loss_type not in L.RECON:
+            raise ValueError(f"Invalid loss type: {loss_type}")          # decoder.py:51
+        L.require_cuda(mean, logvar, target)
+        mean, logvar = _c(mean), _c(logvar)
+        target = _c(target.to(mean.dtype))
+        if target.shape != mean.shape:
+            raise ValueError("target and mean must have the same shape")
+        B, T, C = _btc(mean)
+        elem = torch.empty_like(mean) if want_elem else None
+        out = torch.empty(3, dtype=torch.float32, device=mean.device) if want_mean else None
+        lens_f = _lens(lens, mean) if lens is not None else None
+        if want_mean and lens_f is None:
+            raise ValueError("reduced reconstruction loss needs lens")
+        L.check(L.lib().mlvae_recon_fwd(
+            L.ptr(mean), L.ptr(logvar), L.ptr(target), L.ptr(lens_f), B, T, C, L.dtype_code(mean), L.RECON[loss_type],
+            L.ptr(elem), L.ptr(out), L.ptr(L.reduce_scratch(mean.device)) if want_mean else None, L.stream_ptr()),
+            "mlvae_recon_fwd")
+        ctx.save_for_backward(mean, logvar, target, lens_f)
+        ctx.loss_type = loss_type
+        ctx.need_target = target.requires_grad
+        ctx.set_materialize_grads(False)
+        empty = mean.new_empty(0)
+        return (elem if want_elem else empty), (out[0] if want_mean else empty.float())
+
+    @staticmethod
+    def backward(ctx, gelem, gmean):
+        mean, logvar, target, lens_f = ctx.saved_tensors
+        B, T, C = _btc(mean)
+        gelem = _c(gelem) if gelem is not None and gelem.numel() else None
+        gmean = gmean.contiguous().float() if gmean is not None and gmean.numel() else None
+        gm = torch.empty_like(mean)
+        glv = torch.empty_like(mean) if ctx.loss_type == "likelihood" else None
+        gt = torch.empty_like(mean) if ctx.needs_input_grad[2] else None
+        L.check(L.lib().mlvae_recon_bwd(
+            L.ptr(mean), L.ptr(logvar), L.ptr(target), L.ptr(gelem), L.ptr(gmean), L.ptr(lens_f), B, T, C,
+            L.dtype_code(mean), L.RECON[ctx.loss_type], L.ptr(gm), L.ptr(glv), L.ptr(gt), L.stream_ptr()),
+            "mlvae_recon_bwd")
+        return gm, glv, gt, None, None, None, None
+
+
+def recon_loss(mean, logvar, target, lens=None, loss_type: str = "likelihood",
+               want_elem: bool = False, want_mean: bool = True):
+    """-> (elem | None, masked mean | None)."""
+    e, m = _ReconLoss.apply(mean, logvar, target, lens, loss_type, want_elem, want_mean)
+    return (e if want_elem else None), (m if want_mean else None)
+
+
+class _MaskedReduce(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, loss, lens, reduction):
+        if reduction not in L.RED:
+            raise ValueError(f"Invalid reduction: {reduction}")
+        L.require_cuda(loss)
+        loss = _c(loss)
+        B, T, C = _btc(loss)
+        lens_f = _lens(lens, loss)
+        out = torch.empty(B if reduction == "batch" else 1, dtype=torch.float32, device=loss.device)
+        L.check(L.lib().mlvae_masked_reduce_fwd(
+            L.ptr(loss), L.ptr(lens_f), B, T, C, L.dtype_code(loss), L.RED[reduction], L.ptr(out),
+            L.ptr(L.reduce_scratch(loss.device)), L.stream_ptr()), "mlvae_masked_reduce_fwd")
+        ctx.save_for_backward(lens_f)
+        ctx.meta = (tuple(loss.shape), loss.dtype, reduction, B, T, C)
+        return out if reduction == "batch" else out[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        (lens_f,) = ctx.saved_tensors
+        shape, dtype, reduction, B, T, C = ctx.meta
+        g = g.contiguous().float().reshape(-1)
+        gl = torch.empty(shape, dtype=dtype, device=g.device)
+        L.check(L.lib().mlvae_masked_reduce_bwd(
+            L.ptr(g), L.ptr(lens_f), B, T, C, L.dtype_code(gl), L.RED[reduction], L.ptr(gl), L.stream_ptr()),
+            "mlvae_masked_reduce_bwd")
+        return gl, None, None
+
+
+def masked_reduce(loss, lens, reduction: str = "mean"):
+    return _MaskedReduce.apply(loss, lens, reduction)

@@ -18,9 +18,13 @@ This file is the host restatement of that stream (numpy, vectorised):
     key     = (seed & 0xffffffff, seed >> 32)
     u32[4]  = philox4x32_10(counter, key)
     Box-Muller on pairs: (u32[0], u32[1]) -> normals 0,1 ; (u32[2], u32[3]) -> 2,3
-      u1 = (a + 1) * 2^-32          in (0, 1]
-      u2 = b * 2^-32                in [0, 1)
-      rad = sqrt(-2 ln u1);  n_even = rad * cos(2 pi u2);  n_odd = rad * sin(2 pi u2)
+      u1    = fl32(fl32(a) + 1) * 2^-32               in (0, 1]     (float32 steps, like the kernel)
+      theta = fl32(int32(b)) * fl32(pi * 2^-31)        in [-pi, pi)
+      rad = sqrt(-2 ln u1);  n_even = rad * cos(theta);  n_odd = rad * sin(theta)
+    The kernel evaluates ln/sqrt/sin/cos with the GPU's fast approximations (abs error
+    ~1e-6); this file evaluates them in float64 from the same float32 u1/theta, so the two
+    agree to ~2e-6 absolute -- parity tests that need identical eps materialise it on the
+    device (mlvae_philox_normal) and feed that tensor to the oracle.
 """
 from __future__ import annotations
 
@@ -65,9 +69,9 @@ def philox_u32(seed: int, offset: int, n: int) -> np.ndarray:
 def philox_normal(seed: int, offset: int, n: int, dtype=np.float32) -> np.ndarray:
     """eps stream, computed in float64 and rounded once to ``dtype``."""
     nblk = (n + 3) // 4
-    u = philox_u32(seed, offset, nblk * 4).reshape(nblk, 2, 2).astype(np.float64)
-    u1 = (u[..., 0] + 1.0) * 2.0 ** -32
-    u2 = u[..., 1] * 2.0 ** -32
+    u = philox_u32(seed, offset, nblk * 4).reshape(nblk, 2, 2)
+    u1 = ((u[..., 0].astype(np.float32) + np.float32(1.0)) * np.float32(2.0 ** -32)).astype(np.float64)
+    theta = (u[..., 1].view(np.int32).astype(np.float32) * np.float32(np.pi * 2.0 ** -31)).astype(np.float64)
     rad = np.sqrt(-2.0 * np.log(u1))
-    out = np.stack([rad * np.cos(2.0 * np.pi * u2), rad * np.sin(2.0 * np.pi * u2)], -1)
+    out = np.stack([rad * np.cos(theta), rad * np.sin(theta)], -1)
     return out.reshape(-1)[:n].astype(dtype)

@@ -1,0 +1,133 @@
+"""GPU parity: fused fbank front-end (csrc/fbank.cu through the C ABI) against the oracle
+restatement of SpeechBrain Fbank (oracle/fbank_ref.py; PARITY UNPINNED against SpeechBrain
+itself, see oracle/__init__.py) and the committed fixtures.
+
+Tolerance: the feature values are dB (10*log10), so the stated fp32 bound 1e-5 rel is applied
+as |a-b| <= 1e-5*(|b| + max|b|) -- about 1e-3 dB for ~50 dB dynamic range -- and checked
+against the float64 oracle (the float32 torch.stft oracle itself is ~1e-4 dB away from it)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from _util import BF16_RTOL, FP32_RTOL, assert_close
+from conftest import GOLDEN
+from oracle import fbank_ref
+
+pytestmark = pytest.mark.gpu
+
+
+def _fb(**kw):
+    from ml_vae_b200.features import Fbank
+    return Fbank(**kw)
+
+
+def test_golden_fixtures(cuda):
+    z = np.load(os.path.join(GOLDEN, "fbank_cases.npz"))
+    for tag in "abcdef":
+        n, hop_ms, n_mels, dl = [int(v) for v in z[f"{tag}.cfg"]]
+        wav = torch.from_numpy(z[f"{tag}.wav"])[None].to(cuda)
+        fb = _fb(deltas=bool(dl), sample_rate=16000, hop_length=hop_ms, n_fft=400, n_mels=n_mels)
+        full = fb(wav)                                              # SpeechBrain contract: (1, 1+N//hop, D)
+        hop = 16 * hop_ms
+        assert full.shape == (1, 1 + n // hop, n_mels * (3 if dl else 1))
+        feats, rel = fb(wav, torch.tensor([n]), truncate=True)      # data_io.py:199-201 applied
+        want = torch.from_numpy(z[f"{tag}.f64"])
+        assert feats.shape[1] == want.shape[0]                      # frame count: integer exact
+        assert int(round(float(rel[0]) * feats.shape[1])) == want.shape[0]
+        assert_close(feats[0], want, FP32_RTOL, f"fbank_{tag} vs f64 oracle")
+        assert torch.equal(feats[0], full[0, : want.shape[0]])
+        assert_close(feats[0], torch.from_numpy(z[f"{tag}.f32"]), 2e-5, f"fbank_{tag} vs f32 oracle")
+
+
+@pytest.mark.parametrize("hop_ms,n_mels,deltas", [(10, 80, False), (10, 80, True), (20, 40, True), (10, 40, False)])
+def test_batched_ragged_vs_per_utterance_oracle(cuda, hop_ms, n_mels, deltas):
+    """Zero-padded batch with ragged lengths == the reference's per-utterance features
+    (per-utterance top_db floor, per-utterance deltas), zeros past each utterance."""
+    g = torch.Generator().manual_seed(123456)
+    hop = 16 * hop_ms
+    lens = [16000, 15999, 8000 + 3, 4000, 399, 200, 160, 16000 - hop // 2]
+    N = max(lens)
+    wav = torch.zeros(len(lens), N)
+    for b, n in enumerate(lens):
+        wav[b, :n] = 0.1 * torch.randn(n, generator=g) * (1.0 if b % 2 == 0 else 0.01)
+    want, frames = fbank_ref.batched_features(wav, torch.tensor(lens), deltas_=deltas, hop_length=hop_ms,
+                                              n_mels=n_mels, dtype=torch.float64)
+    fb = _fb(deltas=deltas, hop_length=hop_ms, n_mels=n_mels)
+    got, rel = fb(wav.to(cuda), torch.tensor(lens), truncate=True)
+    assert got.shape[1] >= want.shape[1]
+    t = want.shape[1]
+    for b in range(len(lens)):
+        nb = int(frames[b])
+        assert_close(got[b, :nb], want[b, :nb], FP32_RTOL, f"row {b} (len {lens[b]})")
+        assert torch.count_nonzero(got[b, nb:]) == 0
+    # rel lens reproduce the integer frame counts under round(len * T)
+    assert torch.equal(torch.round(rel.cpu() * got.shape[1]).long(), frames)
+    # bf16 output
+    got16, _ = fb(wav.to(cuda), torch.tensor(lens), truncate=True, out_dtype=torch.bfloat16)
+    assert got16.dtype == torch.bfloat16
+    assert_close(got16[:, :t].float(), want, BF16_RTOL, "bf16 features")
+
+
+def test_silence_and_clamp(cuda):
+    """Digital silence -> clamp(1e-10) -> -100 dB everywhere; mixed -> floor at max-80 dB."""
+    fb = _fb(deltas=False, hop_length=10, n_mels=80)
+    out = fb(torch.zeros(1, 3200, device=cuda))
+    assert torch.all(out == -100.0)
+    wav = torch.zeros(1, 6400)
+    wav[0, :1600] = torch.randn(1600, generator=torch.Generator().manual_seed(0))
+    want = fbank_ref.fbank(wav, False, 16000, 10, 400, 80, torch.float64)
+    got = fb(wav.to(cuda))
+    assert_close(got, want, FP32_RTOL, "floor")
+    assert float(got.min()) == pytest.approx(float(want.max()) - 80.0, abs=1e-3)
+
+
+def test_linearity_property_full_size(cuda):
+    """BASELINE config-2 size (64 x 5 s): scaling the waveform by 10 shifts every log-mel by
+    exactly 20 dB (power x100) and leaves deltas unchanged; frame count T = 500."""
+    g = torch.Generator().manual_seed(1)
+    wav = (0.05 * torch.randn(64, 80000, generator=g)).to(cuda)
+    fb = _fb(deltas=True, hop_length=10, n_mels=80)
+    a, rel = fb(wav, torch.full((64,), 80000), truncate=True)
+    b, _ = fb(wav * 10.0, torch.full((64,), 80000), truncate=True)
+    assert a.shape == (64, 500, 240) and torch.all(rel == 1.0)
+    assert (b[..., :80] - a[..., :80] - 20.0).abs().max() < 2e-3
+    assert (b[..., 80:] - a[..., 80:]).abs().max() < 2e-3
+    # long-utterance config 4: 16 x 20 s -> 2000 frames
+    wav = (0.05 * torch.randn(2, 320000, generator=g)).to(cuda)
+    c, _ = _fb(deltas=False, hop_length=10, n_mels=80)(wav, torch.full((2,), 320000), truncate=True)
+    assert c.shape == (2, 2000, 80)
+    ref = fbank_ref.audio_pipeline_features(wav[0].cpu(), False, 16000, 10, 400, 80, torch.float64)
+    assert_close(c[0], ref, FP32_RTOL, "20 s utterance")
+
+
+def test_unsupported_configs_fail_loudly(cuda):
+    with pytest.raises(NotImplementedError):
+        _fb(n_fft=512)
+    with pytest.raises(NotImplementedError):
+        _fb(context=True)
+    from ml_vae_b200._lib import MlvaeError
+    with pytest.raises(MlvaeError, match="no CPU fallback"):
+        _fb()(torch.zeros(1, 1600))
+
+
+def test_internal_tables_match_torch(cuda):
+    """The C library's own window / mel construction (used by non-Python hosts) agrees with
+    the torch-built tables the Python host passes in."""
+    import ctypes as C
+    from ml_vae_b200 import _lib as L
+    fb = _fb(deltas=False, hop_length=10, n_mels=80)
+    wav = (0.1 * torch.randn(2, 8000, generator=torch.Generator().manual_seed(2))).to(cuda)
+    a = fb(wav)
+    h = C.c_void_p()
+    L.check(L.lib().mlvae_fbank_plan_create(C.byref(h), 16000, 160, 400, 80, 0, None, None), "plan")
+    out = torch.empty_like(a)
+    scratch = torch.empty(L.lib().mlvae_fbank_scratch_bytes(h, 2, 8000), dtype=torch.uint8, device=cuda)
+    L.check(L.lib().mlvae_fbank_fwd(h, L.ptr(wav), None, 2, 8000, 8000, 0, L.ptr(out), 0, a.shape[1], None,
+                                    L.ptr(scratch), L.stream_ptr()), "fwd")
+    torch.cuda.synchronize()
+    L.lib().mlvae_fbank_plan_destroy(h)
+    fb._get_plan(wav.device)        # re-upload this module's tables (constant memory is shared)
+    fb._destroy()
+    assert (out - a).abs().max() < 1e-3
