@@ -1,0 +1,123 @@
+"""The data-parallel training step of the hot path: fused fbank -> normaliser -> VanillaVAE ->
+Decoder -> masked losses -> backward -> gradient all-reduce -> Adam.
+
+Mirrors, for the test_vanilla_vae recipe, what the reference does per batch in
+  models/md_model.py:54-88    MDModel.fit_batch  (non-AMP branch)
+  models/test_vanilla_vae/model.py:19-55   compute_forward / compute_objectives
+  models/md_model.py:189-213  compute_and_save_losses (loss-weight lookup)
+with the front-end moved into the step and one process per GPU.
+
+B200-first choices
+  * all parameters live in ONE flat float32 arena and all gradients in one flat float32
+    bucket: the data-parallel exchange is a single NCCL all-reduce over NVLink on that
+    bucket (no per-parameter buckets, no copies), and Adam is one fused launch over it;
+  * utterances are sharded by batch across ranks; every rank reduces its own masked-mean
+    loss (what per-module DDP around the reference would do), gradients are averaged;
+  * non-finite loss skips the update on the device (fused-Adam found_inf), no host sync:
+    the reference's check_gradients (md_model.py:82) does the same with a .item() sync.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+from torch import nn
+
+KLD_N_SAMPLES = 2249          # md_model.py:199
+
+
+def loss_weight(hparams: dict, loss_key: str) -> float:
+    """md_model.py:192-201: x_loss -> x_weight (default 1 if absent); keys containing '_kld'
+    are divided by n_samples / batch_size."""
+    wkey = loss_key.replace("_loss", "_weight")
+    w = hparams.get(wkey, 1)
+    if "_kld" in wkey:
+        w = w / (KLD_N_SAMPLES / hparams["batch_size"])
+    return w
+
+
+class FlatArena:
+    """Re-homes every parameter of ``modules`` into one contiguous float32 buffer (and its
+    gradient into one contiguous bucket) without changing names or values."""
+
+    def __init__(self, modules):
+        params, seen = [], set()
+        for m in modules:
+            for p in m.parameters():
+                if id(p) not in seen:
+                    seen.add(id(p))
+                    params.append(p)
+        self.params = params
+        n = sum(p.numel() for p in params)
+        dev = params[0].device
+        self.flat = torch.empty(n, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        off = 0
+        with torch.no_grad():
+            for p in params:
+                k = p.numel()
+                self.flat[off:off + k].copy_(p.reshape(-1))
+                p.data = self.flat[off:off + k].view(p.shape)
+                p.grad = self.grad[off:off + k].view(p.shape)
+                off += k
+        self.master = nn.Parameter(self.flat, requires_grad=True)   # what the optimiser sees
+        self.master.grad = self.grad
+
+    def zero_grad(self):
+        self.grad.zero_()
+
+    def all_reduce_mean(self, world_size: int, group=None):
+        if world_size > 1:
+            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=group)
+            self.grad.mul_(1.0 / world_size)
+
+
+class TrainStep:
+    def __init__(self, fbank, normalizer, encoder, decoder, hparams: dict, lr: float = 1e-3,
+                 compute_dtype=torch.bfloat16, max_grad_norm: float = 5.0, world_size: int = 1,
+                 seed: int = 123456):
+        self.fbank, self.normalizer, self.encoder, self.decoder = fbank, normalizer, encoder, decoder
+        self.hparams = dict(hparams)
+        self.dtype = compute_dtype
+        self.world_size = world_size
+        self.max_grad_norm = max_grad_norm
+        self.arena = FlatArena([encoder, decoder])
+        # optimizer: !name:torch.optim.Adam {lr: 0.001}  (models/test_vanilla_vae/model.yaml:45-47)
+        self.opt = torch.optim.Adam([self.arena.master], lr=lr, fused=True, capturable=True)
+        self.w_kld = loss_weight(self.hparams, "kld_loss")
+        self.w_rec = loss_weight(self.hparams, "recon_loss")
+        self.epoch = 0
+        self.encoder.set_seed(seed)
+        self.encoder.materialize_loss = False
+        self.decoder.materialize_loss = False
+        self.found_inf = torch.zeros((), dtype=torch.float32, device=self.arena.flat.device)
+        self.last = {}
+
+    # -- forward pieces -------------------------------------------------------------------
+    def features(self, wav, wav_lens):
+        feats, rel = self.fbank(wav, wav_lens, truncate=True, out_dtype=torch.float32)
+        return self.normalizer(feats, rel, epoch=self.epoch).to(self.dtype), rel
+
+    def losses(self, feats, rel):
+        eo = self.encoder(feats, lens=rel)
+        do = self.decoder(eo["sampled_h"], feats, lens=rel)
+        kld, rec = eo["kld_loss"], do["recon_loss"]
+        return self.w_kld * kld + self.w_rec * rec, kld, rec
+
+    # -- one training step ----------------------------------------------------------------
+    def step_from_features(self, feats, rel):
+        loss, kld, rec = self.losses(feats, rel)
+        loss.backward()
+        self.arena.all_reduce_mean(self.world_size)
+        # check_gradients [SB-recall]: non-finite loss -> skip the update; clip the global norm
+        torch.nn.utils.clip_grad_norm_([self.arena.master], self.max_grad_norm, foreach=True)
+        self.found_inf.copy_((~torch.isfinite(loss.detach())).float())
+        self.opt.grad_scale, self.opt.found_inf = None, self.found_inf
+        self.opt.step()
+        self.arena.zero_grad()
+        self.last = {"loss": loss.detach(), "kld_loss": kld.detach(), "recon_loss": rec.detach()}
+        return self.last["loss"]
+
+    def step(self, wav, wav_lens):
+        """wav (B, N) float32 on the device, wav_lens (B,) absolute samples or relative lengths."""
+        feats, rel = self.features(wav, wav_lens)
+        return self.step_from_features(feats, rel)
