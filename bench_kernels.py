@@ -1,0 +1,143 @@
+#!/usr/bin/env python
+"""Per-kernel roofline microbenchmarks (BASELINE.json configs[4] sweep + the front-end).
+
+    python bench_kernels.py [--quick] [--out profiles/rNN_kernels.json]
+
+Every kernel is timed alone with CUDA events on the launching stream, after 3 warm-ups, on
+inputs larger than L2 (126 MB) or with a 256 MiB flush write between launches; the achieved
+figure is ALGORITHMIC bytes / time, the denominator is the measured HBM copy
+bandwidth in MEASURED_PEAKS.json.  Sweep cap (stated as SURVEY asks): shapes with more than
+2^31 elements per tensor are skipped so that five live tensors fit comfortably in HBM.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+
+def peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    return float(json.load(open(p))["hbm_gbs"]) if os.path.exists(p) else 6650.0
+
+
+def time_ms(fn, flush, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    ts = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ts.sort()
+    return ts[len(ts) // 2], ts[0]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--out", default="")
+    ap.add_argument("--only", default="")
+    args = ap.parse_args()
+    from ml_vae_b200 import _lib as L
+    from ml_vae_b200 import ops
+    from ml_vae_b200.build import build
+    from ml_vae_b200.features import Fbank
+    build()
+    dev = torch.device("cuda:0")
+    peak = peak_gbs()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    rows = []
+
+    def rec(name, shape, dtype, bytes_, ms_med, ms_min):
+        gbs = bytes_ / (ms_med * 1e-3) / 1e9
+        rows.append({"kernel": name, "shape": shape, "dtype": dtype, "algorithmic_bytes": bytes_,
+                     "ms_median": round(ms_med, 5), "ms_min": round(ms_min, 5), "achieved_gbs": round(gbs, 1),
+                     "frac_of_measured_peak": round(gbs / peak, 4)})
+        print(f"{name:28s} {str(shape):22s} {dtype:5s} {ms_med:9.4f} ms  {gbs:8.1f} GB/s  {gbs / peak:6.1%}", flush=True)
+
+    lat = [(32, 1 << 20), (64, 1 << 20), (64, 4 << 20), (64, 16 << 20), (256, 1 << 20), (256, 4 << 20), (1024, 1 << 20)]
+    if args.quick:
+        lat = [(64, 1 << 20), (64, 4 << 20), (256, 1 << 20)]
+    if not args.only or "latent" in args.only:
+        for dt, s, name in ((torch.bfloat16, 2, "bf16"), (torch.float32, 4, "f32")):
+            for Ld, M in lat:
+                if M * Ld > (1 << 31) or (s == 4 and M * Ld > (1 << 30)):
+                    continue
+                B, T = 64, M // 64
+                mu = torch.randn(B, T, Ld, device=dev, dtype=dt)
+                lv = torch.randn(B, T, Ld, device=dev, dtype=dt).clamp_(-6, 3)
+                gz = torch.randn(B, T, Ld, device=dev, dtype=dt)
+                lens = torch.linspace(0.5, 1.0, B, device=dev)
+                z = torch.empty_like(mu); gmu = torch.empty_like(mu); glv = torch.empty_like(mu)
+                out = torch.empty(3, device=dev)
+                one = torch.ones((), device=dev)
+                sc = L.reduce_scratch(dev)
+                code = L.dtype_code(mu)
+                lib = L.lib()
+                st = L.stream_ptr()
+
+                def fwd():
+                    L.check(lib.mlvae_reparam_kl_fwd(L.ptr(mu), L.ptr(lv), None, 1, 0, L.ptr(lens), B, T, Ld, code,
+                                                     L.ptr(z), None, L.ptr(out), L.ptr(sc), st))
+
+                def bwd():
+                    L.check(lib.mlvae_reparam_kl_bwd(L.ptr(mu), L.ptr(lv), None, 1, 0, L.ptr(gz), None, L.ptr(one),
+                                                     L.ptr(lens), B, T, Ld, code, L.ptr(gmu), L.ptr(glv), st))
+
+                big = M * Ld * s * 3 > (200 << 20)
+                m, mn = time_ms(fwd, None if big else flush)
+                rec("reparam_kl_fwd(philox)", (M, Ld), name, 3 * M * Ld * s, m, mn)
+                m, mn = time_ms(bwd, None if big else flush)
+                rec("reparam_kl_bwd(philox)", (M, Ld), name, 5 * M * Ld * s, m, mn)
+                # reconstruction loss on the same buffers (mean=mu, logvar=lv, target=gz)
+                def rfwd():
+                    L.check(lib.mlvae_recon_fwd(L.ptr(mu), L.ptr(lv), L.ptr(gz), L.ptr(lens), B, T, Ld, code, 0, None,
+                                                L.ptr(out), L.ptr(sc), st))
+
+                def rbwd():
+                    L.check(lib.mlvae_recon_bwd(L.ptr(mu), L.ptr(lv), L.ptr(gz), None, L.ptr(one), L.ptr(lens), B, T, Ld,
+                                                code, 0, L.ptr(gmu), L.ptr(glv), None, st))
+                m, mn = time_ms(rfwd, None if big else flush)
+                rec("recon_nll_fwd", (M, Ld), name, 3 * M * Ld * s, m, mn)
+                m, mn = time_ms(rbwd, None if big else flush)
+                rec("recon_nll_bwd", (M, Ld), name, 5 * M * Ld * s, m, mn)
+                del mu, lv, gz, z, gmu, glv
+                torch.cuda.empty_cache()
+
+    if not args.only or "fbank" in args.only:
+        for (B, secs, hop_ms, mels, dl, od) in [(64, 5, 10, 80, False, torch.float32), (64, 5, 10, 80, True, torch.bfloat16),
+                                                (16, 20, 10, 80, False, torch.float32), (512, 5, 10, 80, False, torch.float32),
+                                                (512, 5, 20, 40, True, torch.float32)]:
+            n = secs * 16000
+            wav = 0.1 * torch.randn(B, n, device=dev)
+            fb = Fbank(deltas=dl, hop_length=hop_ms, n_mels=mels)
+            lens = torch.full((B,), n, dtype=torch.int32, device=dev)
+            hop = 16 * hop_ms
+            T = n // hop
+            D = mels * (3 if dl else 1)
+            s = 2 if od == torch.bfloat16 else 4
+            f = lambda: fb(wav, lens, truncate=True, out_dtype=od)
+            m, mn = time_ms(f, flush)
+            rec("fbank(logmel+finish)", (B, n, f"hop{hop}", f"D{D}"), "bf16" if s == 2 else "f32",
+                B * n * 4 + B * T * D * s, m, mn)
+            del wav
+
+    if args.out:
+        os.makedirs(os.path.dirname(os.path.join(ROOT, args.out)), exist_ok=True)
+        json.dump({"peak_gbs": peak, "rows": rows}, open(os.path.join(ROOT, args.out), "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()

@@ -43,6 +43,7 @@ SIGNATURES = {
 }
 
 _lib = None
+LAUNCHES = 0      # kernels of libmlvae_b200 launched so far (bench.py reads and resets it)
 
 
 class MlvaeError(RuntimeError):
@@ -67,7 +68,9 @@ def lib() -> C.CDLL:
     return _lib
 
 
-def check(rc: int, what: str = ""):
+def check(rc: int, what: str = "", kernels: int = 1):
+    global LAUNCHES
+    LAUNCHES += kernels
     if rc != 0:
         msg = lib().mlvae_last_error()
         raise MlvaeError(f"{what} failed with status {rc}: {msg.decode() if msg else ''}")

@@ -79,7 +79,7 @@ class Fbank(torch.nn.Module):
             with torch.cuda.device(device):
                 L.check(L.lib().mlvae_fbank_plan_create(C.byref(handle), self.sample_rate, self.hop, self.n_fft,
                                                          self.n_mels, int(self.deltas), C.c_void_p(win.data_ptr()),
-                                                         C.c_void_p(mel.data_ptr())), "mlvae_fbank_plan_create")
+                                                         C.c_void_p(mel.data_ptr())), "mlvae_fbank_plan_create", kernels=0)
             self._plan, self._plan_device = handle, device
         return self._plan
 
@@ -125,7 +125,7 @@ class Fbank(torch.nn.Module):
             self._scratch = torch.empty(need, dtype=torch.uint8, device=wav.device)
         L.check(L.lib().mlvae_fbank_fwd(plan, L.ptr(wav), L.ptr(len_dev), B, N, wav.stride(0), int(truncate),
                                         L.ptr(out), L.dtype_code(out), t_out, L.ptr(frames), L.ptr(self._scratch),
-                                        L.stream_ptr()), "mlvae_fbank_fwd")
+                                        L.stream_ptr()), "mlvae_fbank_fwd", kernels=2)
         if wav_lens is None and not truncate:
             return out
         return out, frames.float() / t_out
