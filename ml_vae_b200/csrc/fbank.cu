@@ -54,6 +54,9 @@ struct MelTables {          // device pointers
     int nnz;
 };
 
+// max that propagates NaN like torch.max / torch.clamp / amax do (fmaxf would drop it)
+__device__ __forceinline__ float pmax(float a, float b) { return (a >= b || a != a) ? a : b; }
+
 __device__ __forceinline__ int skew(int p, int s) { return s > 0 ? p + (p >> s) : p; }
 
 // ------------------------------------------------------------------ pass 1 --
@@ -181,18 +184,19 @@ logmel_kernel(const float *__restrict__ wav, const int32_t *__restrict__ wav_len
         const float *wp = s_mw + s_woff[m];
         float acc = 0.f;
         for (int i = 0; i < cnt; ++i) acc = fmaf(s_P[(lo + i) * 32 + lane], wp[i], acc);
-        const float db = kTenLog10Of2 * __log2f(fmaxf(acc, kAmin));
+        const float db = kTenLog10Of2 * __log2f(pmax(acc, kAmin));
         s_O[lane * ostride + m] = db;
-        if (frame_ok) vmax = fmaxf(vmax, db);
+        if (frame_ok) vmax = pmax(vmax, db);
     }
-    vmax = warp_max(vmax);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) vmax = pmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
     __shared__ float s_wmax[kWarps];
     if (lane == 0) s_wmax[warp] = vmax;
     __syncthreads();
     if (tid == 0) {
         float m = s_wmax[0];
 #pragma unroll
-        for (int i = 1; i < kWarps; ++i) m = fmaxf(m, s_wmax[i]);
+        for (int i = 1; i < kWarps; ++i) m = pmax(m, s_wmax[i]);
         atomicMax(max_buf + b, f2ord(m));
     }
     // ---- coalesced tile store: frames [t0, t0 + nf) x n_mels are contiguous in the scratch ----
@@ -225,7 +229,7 @@ finish_kernel(const float *__restrict__ logmel, const unsigned int *__restrict__
     const float floor_db = ord2f(max_buf[b]) - kTopDb;
     const float *x = logmel + (int64_t)b * t_full_max * n_mels + m;
     T *o = out + ((int64_t)b * t_out) * D + m;
-    auto X = [&](int t) { return fmaxf(__ldg(x + (int64_t)min(max(t, 0), t_full - 1) * n_mels), floor_db); };
+    auto X = [&](int t) { return pmax(__ldg(x + (int64_t)min(max(t, 0), t_full - 1) * n_mels), floor_db); };
     // delta at clamped index tau, replicate padding of the input: sum_j j * x[clamp(tau + j)] / 10
     auto DELTA = [&](int tau) {
         tau = min(max(tau, 0), t_full - 1);

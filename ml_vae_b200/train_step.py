@@ -19,8 +19,9 @@ B200-first choices
 from __future__ import annotations
 
 import torch
-import torch.distributed as dist
 from torch import nn
+
+from .parallel import all_reduce_mean_, broadcast_
 
 KLD_N_SAMPLES = 2249          # md_model.py:199
 
@@ -66,9 +67,10 @@ class FlatArena:
         self.grad.zero_()
 
     def all_reduce_mean(self, world_size: int, group=None):
-        if world_size > 1:
-            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=group)
-            self.grad.mul_(1.0 / world_size)
+        all_reduce_mean_(self.grad, world_size, group)
+
+    def broadcast(self, src: int = 0, group=None):
+        broadcast_(self.flat, src, group)
 
 
 class TrainStep:

@@ -1,0 +1,75 @@
+"""CPU, world_size 2, gloo: the N>1 path of the training step -- batch sharding and the
+single flat-bucket gradient all-reduce -- without any kernel call."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from ml_vae_b200.parallel import shard_bounds
+
+
+def test_shard_bounds_cover_batch_exactly():
+    for B in (1, 7, 64, 65, 512):
+        for G in (1, 2, 3, 8):
+            spans = [shard_bounds(B, r, G) for r in range(G)]
+            assert spans[0][0] == 0 and spans[-1][1] == B
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(G - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_bounds(8, 2, 2)
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ml_vae_b200.parallel import shard_batch
+    from ml_vae_b200.train_step import FlatArena
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 1))
+    if rank == 1:                                   # deliberately different start: broadcast must fix it
+        with torch.no_grad():
+            for p in model.parameters():
+                p.add_(1.0)
+    arena = FlatArena([model])
+    arena.broadcast(0)
+    g = torch.Generator().manual_seed(1)
+    x, y = torch.randn(8, 6, generator=g), torch.randn(8, 1, generator=g)
+    xs, ys = shard_batch([x, y], rank, world)
+    loss = ((model(xs) - ys) ** 2).mean()           # local mean over this rank's utterances
+    loss.backward()                                 # accumulates straight into the flat bucket
+    arena.all_reduce_mean(world)
+    if rank == 0:
+        torch.save({"grad": arena.grad.clone(), "flat": arena.flat.clone(), "names": [tuple(p.shape) for p in arena.params]}, out)
+    dist.destroy_process_group()
+
+
+def test_flat_bucket_all_reduce_equals_full_batch_gradient(tmp_path):
+    out = str(tmp_path / "r0.pt")
+    mp.spawn(_worker, args=(2, 29531, out), nprocs=2, join=True)
+    got = torch.load(out)
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 1))
+    g = torch.Generator().manual_seed(1)
+    x, y = torch.randn(8, 6, generator=g), torch.randn(8, 1, generator=g)
+    ((model(x) - y) ** 2).mean().backward()         # equal shards -> mean of local means == global mean
+    ref = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
+    assert torch.allclose(got["grad"], ref, atol=1e-6)
+    assert torch.equal(got["flat"], torch.cat([p.detach().reshape(-1) for p in model.parameters()]))
+
+
+def test_flat_arena_keeps_names_values_and_views():
+    from ml_vae_b200.modules import Decoder, VanillaVAE
+    from ml_vae_b200.train_step import FlatArena
+    torch.manual_seed(3)
+    enc, dec = VanillaVAE([12, 8, 8], 4), Decoder(4, 6, 2, 0.0, [12, 8, 8, 12])
+    before = {k: v.clone() for k, v in list(enc.state_dict().items()) + list(dec.state_dict().items())}
+    arena = FlatArena([enc, dec])
+    after = dict(list(enc.state_dict().items()) + list(dec.state_dict().items()))
+    assert list(before) == list(after) and all(torch.equal(before[k], after[k]) for k in before)
+    assert arena.flat.numel() == sum(v.numel() for v in before.values())
+    arena.flat.zero_()                               # parameters are views of the arena
+    assert all(float(p.abs().sum()) == 0 for p in enc.parameters())
+    assert all(p.grad.data_ptr() >= arena.grad.data_ptr() for p in dec.parameters())
