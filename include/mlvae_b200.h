@@ -168,11 +168,12 @@ int mlvae_fbank_fwd(const mlvae_fbank_plan *plan, const float *d_wav, const int3
                     void *d_scratch, void *stream);
 
 /* ------------------------------------------------------------------------- *
- * tcgen05 / TMEM fused dense stack (modules/fc_block.py:4-21 and the
- * mean/log_var heads of vanilla_vae.py:22-24 and decoder.py:24-25).
- * Declared in mlvae_b200_gemm.h once the kernel lands; round 1 routes the
- * projections through cuBLAS (library) and says so in DESIGN.md.
+ * tcgen05 / TMEM dense projections (modules/fc_block.py:4-21 and the mean/log_var
+ * heads of vanilla_vae.py:22-24 and decoder.py:24-25).
  * ------------------------------------------------------------------------- */
+/* Test hook: D (128 x N, f32) = A (128 x K, bf16) * B (N x K, bf16)^T through one
+ * tcgen05.mma tile; checks the descriptor / TMEM conventions of csrc/tc05.cuh. */
+int mlvae_tc05_selftest(const void *d_a, const void *d_b, float *d_d, int N, int K, void *stream);
 
 #ifdef __cplusplus
 }

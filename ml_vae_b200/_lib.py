@@ -39,6 +39,7 @@ SIGNATURES = {
     "mlvae_fbank_frames": (_i, [_vp, _i64, _i]),
     "mlvae_fbank_feature_dim": (_i, [_vp]),
     "mlvae_fbank_scratch_bytes": (_sz, [_vp, _i, _i64]),
+    "mlvae_tc05_selftest": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "mlvae_fbank_fwd": (_i, [_vp, _vp, _vp, _i, _i64, _i64, _i, _vp, _i, _i, _vp, _vp, _vp]),
 }
 
