@@ -173,7 +173,26 @@ int mlvae_fbank_fwd(const mlvae_fbank_plan *plan, const float *d_wav, const int3
  * ------------------------------------------------------------------------- */
 /* Test hook: D (128 x N, f32) = A (128 x K, bf16) * B (N x K, bf16)^T through one
  * tcgen05.mma tile; checks the descriptor / TMEM conventions of csrc/tc05.cuh. */
-int mlvae_tc05_selftest(const void *d_a, const void *d_b, float *d_d, int N, int K, void *stream);
+int mlvae_tc05_selftest(const void *d_a, const void *d_b, float *d_d, int N, int K, int a_in_tmem, void *stream);
+
+/* ------------------------------------------------------------------------- *
+ * Persistent bidirectional LSTM recurrence (modules/decoder.py:14-15,22: nn.LSTM(batch_first,
+ * bidirectional); one layer per call).  The input projection x W_ih^T + b_ih + b_hh for all
+ * timesteps is a plain GEMM done by the caller into d_p; this entry point walks the T
+ * recurrent steps of BOTH directions in one cooperative launch (tcgen05 + TMEM, W_hh
+ * resident in shared memory).  bf16 only; H % 32 == 0, H <= 704.
+ *   d_p   (B, T, 2, 4H) bf16  gate pre-activations, torch gate order i,f,g,o; when
+ *                             save_gates != 0 it is overwritten with the activated gates
+ *   d_whh (2, 4H, H)    bf16  weight_hh_l{k}, weight_hh_l{k}_reverse
+ *   d_y   (B, T, 2H)    bf16  output (forward direction in [:H], reverse in [H:])
+ *   d_c   (B, T, 2H)    f32   cell states for the backward pass, or NULL
+ *   d_scratch                 mlvae_lstm_scratch_bytes(B) bytes (zeroed by the call)
+ * ------------------------------------------------------------------------- */
+size_t mlvae_lstm_scratch_bytes(int B);
+/* debug: 8 zeroed int64 device counters receiving per-phase cycle totals of CTA 0; NULL disables */
+int mlvae_debug_set_profile_buffer(void *d_prof);
+int mlvae_lstm_fwd(void *d_p, const void *d_whh, void *d_y, float *d_c, int B, int T, int H,
+                   int save_gates, void *d_scratch, void *stream);
 
 #ifdef __cplusplus
 }

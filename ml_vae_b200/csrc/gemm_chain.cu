@@ -26,7 +26,8 @@ __device__ __forceinline__ void load_tile_kmajor(unsigned char *tile, const bf16
 }
 
 __global__ void __launch_bounds__(128, 1)
-tc05_selftest_kernel(const bf16 *__restrict__ A, const bf16 *__restrict__ B, float *__restrict__ D, int N, int K, uint32_t tmem_cols) {
+tc05_selftest_kernel(const bf16 *__restrict__ A, const bf16 *__restrict__ B, float *__restrict__ D, int N, int K, uint32_t tmem_cols,
+                     int a_in_tmem) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t s_bar;
     __shared__ uint32_t s_tmem;
@@ -46,14 +47,30 @@ tc05_selftest_kernel(const bf16 *__restrict__ A, const bf16 *__restrict__ B, flo
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem = s_tmem;
+    const uint32_t a_tmem = tmem + 256;          // A operand columns [256, 256 + K/2) when a_in_tmem
 
+    if (a_in_tmem) {
+        // thread = row m (lane 32*warp + lane): K bf16 of its row -> K/2 packed 32-bit TMEM columns
+        const int m = warp * 32 + lane;
+        for (int k0 = 0; k0 < K; k0 += 16) {
+            const uint4 lo = __ldg(reinterpret_cast<const uint4 *>(A + (int64_t)m * K + k0));
+            const uint4 hi = __ldg(reinterpret_cast<const uint4 *>(A + (int64_t)m * K + k0 + 8));
+            const uint32_t v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+            tc::tmem_st8(a_tmem + ((uint32_t)(warp * 32) << 16) + k0 / 2, v);
+        }
+        tc::tmem_st_wait();
+        tc::fence_before_sync();
+        __syncthreads();
+        tc::fence_after_sync();
+    }
     if (tid == 0) {
         const uint32_t idesc = tc::idesc_bf16_f32(128, N);
         const uint32_t sbo = (uint32_t)(K >> 3) * 128;
         for (int k = 0; k < K / 16; ++k) {
             const uint64_t da = tc::smem_desc(tc::smem_u32(sA) + k * 256, 128, sbo);
             const uint64_t db = tc::smem_desc(tc::smem_u32(sB) + k * 256, 128, sbo);
-            tc::mma_bf16(tmem, da, db, idesc, k > 0);
+            if (a_in_tmem) tc::mma_bf16_ts(tmem, a_tmem + k * 8, db, idesc, k > 0);
+            else tc::mma_bf16(tmem, da, db, idesc, k > 0);
         }
         tc::mma_commit(&s_bar);
     }
@@ -81,15 +98,19 @@ extern "C" {
 
 // D (128 x N, float32) = A (128 x K, bf16 row-major) * B (N x K, bf16 row-major)^T.  N % 16 == 0, N <= 256,
 // K % 16 == 0, (128 + N) * K * 2 <= 200 KB.  Test hook for the descriptor conventions in tc05.cuh.
-int mlvae_tc05_selftest(const void *d_a, const void *d_b, float *d_d, int N, int K, void *stream) {
+int mlvae_tc05_selftest(const void *d_a, const void *d_b, float *d_d, int N, int K, int a_in_tmem, void *stream) {
     MLVAE_REQUIRE(d_a && d_b && d_d, MLVAE_ERR_INVALID_ARG, "tc05_selftest: null buffer");
     MLVAE_REQUIRE(N >= 16 && N <= 256 && N % 16 == 0 && K >= 16 && K % 16 == 0, MLVAE_ERR_INVALID_ARG, "tc05_selftest: bad N/K");
     const size_t smem = (size_t)(128 + N) * K * 2;
     MLVAE_REQUIRE(smem <= 200 * 1024, MLVAE_ERR_UNSUPPORTED, "tc05_selftest: tile too large");
     uint32_t cols = 32;
     while ((int)cols < N) cols <<= 1;
+    if (a_in_tmem) {
+        MLVAE_REQUIRE(K <= 512, MLVAE_ERR_UNSUPPORTED, "tc05_selftest: A-in-TMEM needs K <= 512");
+        cols = 512;
+    }
     MLVAE_CHECK_CUDA(cudaFuncSetAttribute(tc05_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tc05_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>((const bf16 *)d_a, (const bf16 *)d_b, d_d, N, K, cols);
+    tc05_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>((const bf16 *)d_a, (const bf16 *)d_b, d_d, N, K, cols, a_in_tmem);
     MLVAE_CHECK_CUDA(cudaGetLastError());
     return MLVAE_OK;
 }

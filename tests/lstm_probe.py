@@ -1,0 +1,77 @@
+"""Stand-alone probe of the persistent LSTM forward (run under `timeout`)."""
+import sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from ml_vae_b200 import _lib as L
+
+dev = torch.device("cuda:0")
+torch.backends.cuda.matmul.allow_tf32 = False
+torch.backends.cudnn.allow_tf32 = False
+
+
+def run(B, T, In, H, time_it=False):
+    torch.manual_seed(B * 7 + T + H)
+    lstm = torch.nn.LSTM(In, H, 1, bidirectional=True, batch_first=True).to(dev)
+    with torch.no_grad():
+        for p_ in lstm.parameters():
+            p_.copy_(p_.bfloat16().float())
+    x = torch.randn(B, T, In, device=dev).bfloat16().float()
+    with torch.no_grad():
+        ref, (hn, cn) = lstm(x)
+    wih = torch.cat([lstm.weight_ih_l0, lstm.weight_ih_l0_reverse], 0)                   # (8H, In)
+    bias = torch.cat([lstm.bias_ih_l0 + lstm.bias_hh_l0, lstm.bias_ih_l0_reverse + lstm.bias_hh_l0_reverse], 0)
+    P = (x @ wih.t() + bias).bfloat16().contiguous()                                         # (B, T, 8H) = (B,T,2,4H)
+    whh = torch.stack([lstm.weight_hh_l0, lstm.weight_hh_l0_reverse], 0).bfloat16().contiguous()
+    Y = torch.full((B, T, 2 * H), float("nan"), device=dev, dtype=torch.bfloat16)
+    C = torch.empty(B, T, 2 * H, device=dev)
+    scratch = torch.empty(L.lib().mlvae_lstm_scratch_bytes(B), dtype=torch.uint8, device=dev)
+    P0 = P.clone()
+    L.check(L.lib().mlvae_lstm_fwd(L.ptr(P), L.ptr(whh), L.ptr(Y), L.ptr(C), B, T, H, 1, L.ptr(scratch), L.stream_ptr()), "lstm_fwd")
+    torch.cuda.synchronize()
+    err = float((Y.float() - ref).abs().max() / ref.abs().max())
+    cerr = float((C[:, -1, :H] - cn[0]).abs().max() / cn[0].abs().max())
+    print(f"B={B} T={T} In={In} H={H}: y rel err {err:.3e}  c_T rel err {cerr:.3e}", "OK" if err < 2e-2 else "MISMATCH", flush=True)
+    if time_it:
+        prof = torch.zeros(8, dtype=torch.int64, device=dev)
+        L.check(L.lib().mlvae_debug_set_profile_buffer(L.ptr(prof)), "prof")
+        L.check(L.lib().mlvae_lstm_fwd(L.ptr(P), L.ptr(whh), L.ptr(Y), L.ptr(C), B, T, H, 1, L.ptr(scratch), L.stream_ptr()), "lstm_fwd")
+        torch.cuda.synchronize()
+        L.check(L.lib().mlvae_debug_set_profile_buffer(None), "prof")
+        names = ["flag wait", "h gather", "mma", "tmem+act+save", "cell+store", "fence+publish"]
+        pc = prof.cpu().tolist()
+        print("   cycles/step:", {n: round(v / T) for n, v in zip(names, pc)}, "total", round(sum(pc) / T))
+        for sv in (0, 1):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(3):
+                L.check(L.lib().mlvae_lstm_fwd(L.ptr(P), L.ptr(whh), L.ptr(Y), L.ptr(C) if sv else None, B, T, H, sv, L.ptr(scratch), L.stream_ptr()), "lstm_fwd")
+            b.record(); torch.cuda.synchronize()
+            print(f"   save={sv}: {a.elapsed_time(b) / 3:.3f} ms")
+        for _ in range(2):
+            P.copy_(P0)
+            L.check(L.lib().mlvae_lstm_fwd(L.ptr(P), L.ptr(whh), L.ptr(Y), L.ptr(C), B, T, H, 1, L.ptr(scratch), L.stream_ptr()), "lstm_fwd")
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(5):
+            L.check(L.lib().mlvae_lstm_fwd(L.ptr(P), L.ptr(whh), L.ptr(Y), L.ptr(C), B, T, H, 1, L.ptr(scratch), L.stream_ptr()), "lstm_fwd")
+        b.record(); torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / 5
+        xb = x.bfloat16(); lb = lstm.bfloat16()
+        with torch.no_grad():
+            for _ in range(2): lb(xb)
+            torch.cuda.synchronize(); a.record()
+            for _ in range(3): lb(xb)
+            b.record(); torch.cuda.synchronize()
+        print(f"   persistent kernel {ms:.3f} ms ({ms / T * 1e3:.2f} us/step) vs cuDNN bf16 fwd {a.elapsed_time(b) / 3:.3f} ms", flush=True)
+    return err < 2e-2
+
+
+ok = True
+ok &= run(4, 6, 16, 32)
+ok &= run(16, 20, 24, 64)
+ok &= run(20, 33, 64, 128)
+ok &= run(64, 50, 64, 512)
+ok &= run(64, 500, 64, 512, time_it=True)
+ok &= run(64, 500, 1024, 512, time_it=True)
+print("ALL OK" if ok else "FAILED")
