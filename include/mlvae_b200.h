@@ -186,11 +186,13 @@ int mlvae_tc05_selftest(const void *d_a, const void *d_b, float *d_d, int N, int
  *   d_whh (2, 4H, H)    bf16  weight_hh_l{k}, weight_hh_l{k}_reverse
  *   d_y   (B, T, 2H)    bf16  output (forward direction in [:H], reverse in [H:])
  *   d_c   (B, T, 2H)    f32   cell states for the backward pass, or NULL
- *   d_scratch                 mlvae_lstm_scratch_bytes(B) bytes (zeroed by the call)
+ *   d_scratch                 mlvae_lstm_scratch_bytes(B, H) bytes (zeroed by the call)
  * ------------------------------------------------------------------------- */
-size_t mlvae_lstm_scratch_bytes(int B);
+size_t mlvae_lstm_scratch_bytes(int B, int H);
 /* debug: 8 zeroed int64 device counters receiving per-phase cycle totals of CTA 0; NULL disables */
 int mlvae_debug_set_profile_buffer(void *d_prof);
+/* debug / tuning knobs: key 1 = MMA issuer warps of the LSTM kernels (1, 2, 4) */
+int mlvae_debug_set_option(int key, int value);
 int mlvae_lstm_fwd(void *d_p, const void *d_whh, void *d_y, float *d_c, int B, int T, int H,
                    int save_gates, void *d_scratch, void *stream);
 

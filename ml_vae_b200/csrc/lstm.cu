@@ -2,17 +2,21 @@
 // 2 x biLSTM(512): modules/decoder.py:14-15,22).  cuDNN runs one GEMM + one cell kernel per
 // timestep (2 x T launches per direction-layer); here ONE cooperative launch walks all T steps.
 //
-// Work split.  A "group" = (direction d, batch slice s of NB rows).  Its G = H/32 CTAs each own 32
-// hidden units = 128 gate rows (row = gate*32 + unit) of W_hh, resident in shared memory for the
-// whole sequence (128 x H bf16, K-major).  Per step every CTA computes
-//     D[128 gate rows x NB batch] = W_slice (smem) x h_{t-1}^T (smem)        tcgen05.mma, fp32 in TMEM
-// adds the precomputed input projection P[b, t] (x W_ih^T + b_ih + b_hh, one big GEMM done before),
-// applies the gate non-linearities, updates c (registers) and writes its 32-unit slice of h_t straight
-// into the output tensor Y[b, t, d*H + units].  Y doubles as the exchange buffer: the group's CTAs
-// publish "step done" through one global counter (release: __syncthreads + __threadfence + atomicAdd,
-// acquire: ld.acquire.gpu poll) and then gather h_t (NB x H bf16 = 16 KB at NB = 16) from L2 with
-// cp.async into the K-major B-operand tile.  No data-path atomics, deterministic.
-// All CTAs must be co-resident (they wait on each other): the launch is cooperative.
+// Work split.  A "group" = (direction d, batch slice of NB rows).  Its G = H/32 CTAs each own 32
+// hidden units = 128 gate rows (row = gate*32 + unit) of W_hh.  The slice (128 x H bf16) is loaded
+// ONCE into TENSOR MEMORY (H/2 32-bit columns) and stays there for the whole sequence, so the
+// per-step MMA
+//     D[128 gate rows x NB batch] (TMEM, fp32) = W_slice (TMEM) x h_{t-1}^T (smem, K-major)
+// does not stream 128 KB of weights through shared memory (v1 did: 2700 cycles/step; the TMEM-A
+// form is bounded by 128*NB/256 cycles per K=16 instruction).  The input projection
+// P = x W_ih^T + b_ih + b_hh for all timesteps is one big GEMM done before the launch.
+//
+// Exchange of h_t inside a group uses a flag-in-data protocol over L2 (no fence / atomic / poll
+// round trips): every producer stores 8-byte words {2 x bf16 h, step tag}; 8-byte stores are
+// single transactions, so a consumer that reads tag == step has the data.  Consumers poll their
+// NB x H/2 words with volatile loads, write the bf16 pairs into the K-major B-operand tile, and
+// one elected thread issues the H/16 tcgen05.mma instructions.  Deterministic; no data atomics.
+// All CTAs wait on each other, so the launch is cooperative (co-residency guaranteed or refused).
 #include <cooperative_groups.h>
 
 #include "common.cuh"
@@ -24,15 +28,19 @@ namespace {
 using bf16 = __nv_bfloat16;
 constexpr int kUnits = 32;            // hidden units per CTA
 constexpr int kRows = 4 * kUnits;     // gate rows per CTA == MMA M
-constexpr int kLstmThreads = 128;
+constexpr int kLstmThreads = 512;
+constexpr int kLstmWarps = kLstmThreads / 32;
 
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + __expf(-x)); }
 __device__ __forceinline__ float tanh_f(float x) { return 2.f / (1.f + __expf(-2.f * x)) - 1.f; }
 
-__device__ __forceinline__ unsigned int ld_acquire(const unsigned int *p) {
-    unsigned int v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+__device__ __forceinline__ uint2 ld_volatile_u2(const uint2 *p) {
+    uint2 v;
+    asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
     return v;
+}
+__device__ __forceinline__ void st_volatile_u2(uint2 *p, uint2 v) {
+    asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
 }
 
 __device__ long long *g_prof = nullptr;     // optional per-phase cycle counters (debug / profiles/)
@@ -47,163 +55,233 @@ struct LstmFwdParams {
     const bf16 *Whh;         // (2, 4H, H)
     bf16 *Y;                 // (B, T, 2H)
     float *C;                // (B, T, 2H) cell states (saved for backward) or nullptr
-    unsigned int *flags;     // (2 * n_slices) zeroed counters
+    uint2 *ll;               // [2 parity][2 * slices groups][NB][H/2] zeroed {data, tag} words
     int B, T, H, save;
 };
 
-template <int NB>
+template <int NB, int NCH>
 __global__ void __launch_bounds__(kLstmThreads, 1) lstm_fwd_kernel(LstmFwdParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t s_bar;
     __shared__ uint32_t s_tmem;
     const int H = p.H, T = p.T, B = p.B;
-    const int G = H / kUnits;
-    const int u = blockIdx.x;                     // unit slice (gridDim.x == G)
+    const int u = blockIdx.x;                     // unit slice (gridDim.x == H / 32)
     const int slice = blockIdx.y;                 // batch slice
     const int d = blockIdx.z;                     // direction
     const int b0 = slice * NB;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q = warp & 3;                       // TMEM lane group of this warp == gate (i, f, g, o)
+    const int part = warp >> 2;                   // which quarter of the columns this warp handles
+    constexpr int CPW = NB / 4;                   // accumulator columns (batch rows) per warp
+    constexpr int IPT = NB * kUnits / kLstmThreads;   // (batch row, unit) cell items per thread
+    // NCH issuer warps, each feeding its own accumulator tile with the K steps k = w (mod NCH): issuing the
+    // H/16 small MMAs from one thread is instruction-issue bound (descriptor arithmetic on the uniform
+    // datapath), while more tiles cost TMEM read bandwidth in the epilogue (64 B/cycle).
 
-    unsigned char *sW = smem;                                  // 128 x H bf16, K-major
-    unsigned char *sH = smem + (size_t)kRows * H * 2;          // NB x H bf16, K-major
-    float *s_act = reinterpret_cast<float *>(sH + (size_t)NB * H * 2);   // [4][NB][32]
+    unsigned char *sH = smem;                                               // NB x H bf16, K-major
+    float *s_act = reinterpret_cast<float *>(smem + (size_t)NB * H * 2);    // [4][NB][32]
 
-    if (warp == 0) tc::tmem_alloc(&s_tmem, NB < 32 ? 32 : NB);
+    const uint32_t dcol = (uint32_t)((H / 2 + 31) & ~31);                   // accumulator columns start
+    uint32_t tmem_cols = 32;
+    while (tmem_cols < dcol + 128) tmem_cols <<= 1;
+    if (warp == 0) tc::tmem_alloc(&s_tmem, tmem_cols);
     if (tid == 0) {
-        tc::mbar_init(&s_bar, 1);
+        tc::mbar_init(&s_bar, NCH);
         tc::fence_barrier_init();
     }
-    // ---- resident weight slice: row r = gate*32 + unit  <-  W_hh[d][gate*H + u*32 + unit][:] ----
-    {
-        const int chunks = H >> 3;
-        const bf16 *Wd = p.Whh + (size_t)d * 4 * H * H;
-        for (int i = tid; i < kRows * chunks; i += kLstmThreads) {
-            const int r = (i & 7) | ((i / (8 * chunks)) << 3);
-            const int c = (i >> 3) % chunks;
-            const int grow = (r >> 5) * H + u * kUnits + (r & 31);
-            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(Wd + (size_t)grow * H + c * 8));
-            *reinterpret_cast<uint4 *>(sW + tc::kmajor_off(r, c * 8, H)) = v;
-        }
-    }
-    tc::fence_proxy_async();
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem = s_tmem;
-    const uint32_t idesc = tc::idesc_bf16_f32(kRows, NB);
-    const uint32_t sbo = (uint32_t)(H >> 3) * 128;
-    unsigned int *flag = p.flags + (d * gridDim.y + slice);
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
 
-    constexpr int RPT = NB / 4;                 // batch rows per thread in the cell phase
-    float c_state[RPT];
-#pragma unroll
-    for (int j = 0; j < RPT; ++j) c_state[j] = 0.f;
-
-    const size_t p_row = (size_t)2 * 4 * H;     // elements per (b, t) in P
-    const int gate_col = warp * H + u * kUnits + lane;          // this thread's gate row inside a (b,t,d) block
-
-    long long *prof = (g_prof && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? g_prof : nullptr;
-    long long tprev = clock64();
-    for (int step = 0; step < T; ++step) {
-        const int t = d ? (T - 1 - step) : step;
-        const int t_prev = d ? (t + 1) : (t - 1);
-        // ---- prefetch the input-projection terms for (gate = warp, unit = lane), all NB batch rows ----
-        float pre[NB];
-#pragma unroll
-        for (int j = 0; j < NB; ++j) {
-            const int b = b0 + j;
-            pre[j] = (b < B) ? __bfloat162float(p.P[((size_t)b * T + t) * p_row + (size_t)d * 4 * H + gate_col]) : 0.f;
+    // ---- resident weights: row (gate q, unit lane) of W_hh[d] -> TMEM lane 32q+lane, columns k/2 ----
+    {
+        const bf16 *wrow = p.Whh + ((size_t)d * 4 * H + (size_t)q * H + u * kUnits + lane) * H;
+        for (int k16 = part; k16 < H / 16; k16 += 4) {
+            const uint4 lo = __ldg(reinterpret_cast<const uint4 *>(wrow + k16 * 16));
+            const uint4 hi = __ldg(reinterpret_cast<const uint4 *>(wrow + k16 * 16 + 8));
+            const uint32_t v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+            tc::tmem_st8(tmem + lane_base + k16 * 8, v);
         }
-        float acc[NB];
-        if (step > 0) {
-            // ---- wait for the whole group to have published h_{t_prev}, then gather it from L2 ----
-            if (tid == 0) {
-                const unsigned int target = (unsigned int)G * (unsigned int)step;
-                while (ld_acquire(flag) < target) { }
-            }
-            __syncthreads();
-            PROF_MARK(0);                               // flag wait
-            const int chunks = H >> 3;
-            for (int i = tid; i < NB * chunks; i += kLstmThreads) {
-                const int r = (i & 7) | ((i / (8 * chunks)) << 3);
-                const int c = (i >> 3) % chunks;
-                const int b = b0 + r;
-                const bf16 *src = p.Y + ((size_t)(b < B ? b : 0) * T + t_prev) * (2 * H) + d * H + c * 8;
-                tc::cp_async16(sH + tc::kmajor_off(r, c * 8, H), src, b < B ? 16u : 0u);
-            }
-            tc::cp_async_commit();
-            tc::cp_async_wait<0>();
-            tc::fence_proxy_async();
-            tc::fence_before_sync();
-            __syncthreads();
-            PROF_MARK(1);                               // h gather
-            if (tid == 0) {
-                tc::fence_after_sync();
-                const uint32_t a0 = tc::smem_u32(sW), h0 = tc::smem_u32(sH);
-                for (int k = 0; k < H / 16; ++k)
-                    tc::mma_bf16(tmem, tc::smem_desc(a0 + k * 256, 128, sbo), tc::smem_desc(h0 + k * 256, 128, sbo), idesc, k > 0);
-                tc::mma_commit(&s_bar);
-            }
-            tc::mbar_wait(&s_bar, (step - 1) & 1);
-            tc::fence_after_sync();
-            PROF_MARK(2);                               // MMA issue + completion
-#pragma unroll
-            for (int c0 = 0; c0 < NB; c0 += 16) {
-                uint32_t v[16];
-                tc::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
-                tc::tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 16; ++j) acc[c0 + j] = __uint_as_float(v[j]);
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < NB; ++j) acc[j] = 0.f;       // h_0 = 0
-        }
-        // ---- gate non-linearity (warp 0: i, 1: f, 2: g (tanh), 3: o) ----
-#pragma unroll
-        for (int j = 0; j < NB; ++j) {
-            const float x = acc[j] + pre[j];
-            const float a = (warp == 2) ? tanh_f(x) : sigmoid_f(x);
-            s_act[(warp * NB + j) * 32 + lane] = a;
-            if (p.save && b0 + j < B)
-                p.P[((size_t)(b0 + j) * T + t) * p_row + (size_t)d * 4 * H + gate_col] = __float2bfloat16_rn(a);
-        }
-        tc::fence_before_sync();
-        __syncthreads();
-        PROF_MARK(3);                                   // tmem load + P add + activation (+ gate save)
-        // ---- cell update: thread = (unit = lane, batch rows warp*RPT ...) ----
-#pragma unroll
-        for (int j = 0; j < RPT; ++j) {
-            const int jj = warp * RPT + j;
-            const int b = b0 + jj;
-            const float gi = s_act[(0 * NB + jj) * 32 + lane], gf = s_act[(1 * NB + jj) * 32 + lane];
-            const float gg = s_act[(2 * NB + jj) * 32 + lane], go = s_act[(3 * NB + jj) * 32 + lane];
-            const float c = gf * c_state[j] + gi * gg;
-            c_state[j] = c;
-            const float h = go * tanh_f(c);
-            if (b < B) {
-                const size_t o = ((size_t)b * T + t) * (2 * H) + d * H + u * kUnits + lane;
-                p.Y[o] = __float2bfloat16_rn(h);
-                if (p.C) p.C[o] = c;
-            }
-        }
-        __syncthreads();
-        PROF_MARK(4);                                   // cell update + Y / C stores
-        if (tid == 0) {
-            __threadfence();
-            atomicAdd(flag, 1u);
-        }
-        PROF_MARK(5);                                   // fence + publish
+        tc::tmem_st_wait();
     }
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tmem, NB < 32 ? 32 : NB);
+    tc::fence_after_sync();
+
+    const uint32_t idesc = tc::idesc_bf16_f32(kRows, NB);
+    const uint32_t sbo = (uint32_t)(H >> 3) * 128;
+    const int groups = 2 * gridDim.y;
+    const int group = d * gridDim.y + slice;
+    const size_t ll_words = (size_t)NB * (H / 2);
+    const int n_words = NB * (H / 2);
+
+    float c_state[IPT];
+#pragma unroll
+    for (int j = 0; j < IPT; ++j) c_state[j] = 0.f;
+
+    const size_t p_row = (size_t)2 * 4 * H;                              // elements per (b, t) in P
+    const size_t gate_col = (size_t)d * 4 * H + (size_t)q * H + u * kUnits + lane;
+    auto p_index = [&](int j, int t) { return ((size_t)(b0 + j) * T + t) * p_row + gate_col; };
+
+    // input-projection terms are prefetched one step ahead as RAW bf16 bits: converting at load time
+    // would stall the warp on the DRAM latency inside the step
+    const unsigned short *P16 = reinterpret_cast<const unsigned short *>(p.P);
+    unsigned short pre_raw[CPW];
+    {
+        const int t0 = d ? (T - 1) : 0;
+#pragma unroll
+        for (int i = 0; i < CPW; ++i) {
+            const int j = part * CPW + i;
+            pre_raw[i] = P16[p_index(min(j, B - 1 - b0), t0)];      // rows past B: clamp (their results are never stored)
+        }
+    }
+    long long *prof = (g_prof && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? g_prof : nullptr;
+    long long tprev = clock64();
+
+    for (int step = 0; step < T; ++step) {
+        const int t = d ? (T - 1 - step) : step;
+        float acc[CPW];
+        if (step > 0) {
+            // ---- gather h_{t_prev}: poll the {data, tag} words of this group, tag == step ----
+            const uint2 *src = p.ll + ((size_t)(step & 1) * groups + group) * ll_words;
+            constexpr int WB = 8;                        // words per thread per round
+            for (int i0 = tid; i0 < n_words; i0 += kLstmThreads * WB) {
+                uint2 w[WB];
+                // spin on ONE word per thread (light polling traffic), then fetch the rest and re-check
+                w[0] = ld_volatile_u2(src + i0);
+                while (w[0].y != (uint32_t)step) w[0] = ld_volatile_u2(src + i0);
+#pragma unroll
+                for (int n = 1; n < WB; ++n) {
+                    const int i = i0 + n * kLstmThreads;
+                    if (i < n_words) w[n] = ld_volatile_u2(src + i);
+                }
+#pragma unroll
+                for (int n = 1; n < WB; ++n) {
+                    const int i = i0 + n * kLstmThreads;
+                    if (i < n_words)
+                        while (w[n].y != (uint32_t)step) w[n] = ld_volatile_u2(src + i);
+                }
+#pragma unroll
+                for (int n = 0; n < WB; ++n) {
+                    const int i = i0 + n * kLstmThreads;
+                    if (i >= n_words) continue;
+                    const int j = i / (H / 2), kw = i - j * (H / 2);
+                    *reinterpret_cast<uint32_t *>(sH + tc::kmajor_off(j, 2 * kw, H)) = w[n].x;
+                }
+            }
+            tc::fence_proxy_async();
+            tc::fence_before_sync();
+            __syncthreads();
+            PROF_MARK(0);                               // gather (includes waiting for the slowest producer)
+            if (warp < NCH) {                            // warp-uniform: issuer warps
+                if (tc::elect_one()) {
+                    tc::fence_after_sync();
+                    const uint64_t b_desc0 = tc::smem_desc(tc::smem_u32(sH), 128, sbo);
+                    const uint32_t d_tile = tmem + dcol + warp * NB;
+#pragma unroll 4
+                    for (int k = warp; k < H / 16; k += NCH)
+                        tc::mma_bf16_ts(d_tile, tmem + k * 8, b_desc0 + (uint64_t)(k * 16), idesc, k >= NCH);
+                    tc::mma_commit(&s_bar);
+                }
+                __syncwarp();
+            }
+            tc::mbar_wait(&s_bar, (step - 1) & 1);
+            tc::fence_after_sync();
+            PROF_MARK(1);                               // MMA issue + completion
+            uint32_t v[NCH][CPW];
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) tc::tmem_ld<CPW>(tmem + lane_base + dcol + c * NB + part * CPW, v[c]);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < CPW; ++i) {
+                float a = 0.f;
+#pragma unroll
+                for (int c = 0; c < NCH; ++c)
+                    if (c < H / 16) a += __uint_as_float(v[c][i]);
+                acc[i] = a;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < CPW; ++i) acc[i] = 0.f;      // h_0 = 0
+        }
+        // ---- gate non-linearity: warp group q = 0: i, 1: f, 2: g (tanh), 3: o ----
+#pragma unroll
+        for (int i = 0; i < CPW; ++i) {
+            const int j = part * CPW + i;
+            const float x = acc[i] + __uint_as_float((uint32_t)pre_raw[i] << 16);
+            const float a = (q == 2) ? tanh_f(x) : sigmoid_f(x);
+            s_act[(q * NB + j) * 32 + lane] = a;
+            if (p.save && b0 + j < B) p.P[p_index(j, t)] = __float2bfloat16_rn(a);
+        }
+        if (step + 1 < T) {                              // prefetch next step's input projection
+            const int tn = d ? (t - 1) : (t + 1);
+#pragma unroll
+            for (int i = 0; i < CPW; ++i) {
+                const int j = part * CPW + i;
+                pre_raw[i] = P16[p_index(min(j, B - 1 - b0), tn)];
+            }
+        }
+        tc::fence_before_sync();
+        __syncthreads();
+        PROF_MARK(2);                                   // tmem load + activation
+        // ---- cell update + publish: thread = (batch row j, unit = lane) ----
+        uint2 *dst = p.ll + ((size_t)((step + 1) & 1) * groups + group) * ll_words;
+#pragma unroll
+        for (int it = 0; it < IPT; ++it) {
+            const int j = warp + it * kLstmWarps;
+            const int b = b0 + j;
+            const float gi = s_act[(0 * NB + j) * 32 + lane], gf = s_act[(1 * NB + j) * 32 + lane];
+            const float gg = s_act[(2 * NB + j) * 32 + lane], go = s_act[(3 * NB + j) * 32 + lane];
+            const float c = gf * c_state[it] + gi * gg;
+            c_state[it] = c;
+            const float h = go * tanh_f(c);
+            const bf16 hb = __float2bfloat16_rn(h);
+            const uint32_t mine = (uint32_t)__bfloat16_as_ushort(hb);
+            const uint32_t other = __shfl_down_sync(0xffffffffu, mine, 1);
+            if (!(lane & 1) && step + 1 < T)
+                st_volatile_u2(dst + (size_t)j * (H / 2) + (u * kUnits + lane) / 2, make_uint2(mine | (other << 16), (uint32_t)(step + 1)));
+            if (b < B) {
+                const size_t o = ((size_t)b * T + t) * (2 * H) + d * H + u * kUnits + lane;
+                p.Y[o] = hb;
+                if (p.C) p.C[o] = c;
+            }
+        }
+        PROF_MARK(3);                                   // cell update + stores
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, tmem_cols);
 }
 
 }  // namespace
 }  // namespace mlvae
 
 using namespace mlvae;
+
+namespace {
+int g_lstm_issuers = 2;      // tuning knob (mlvae_debug_set_option key 1)
+int g_lstm_min_nb = 16;      // tuning knob (key 2): smallest batch slice per CTA
+struct LstmPlan {
+    int NB, slices, G;
+    size_t smem, ll_bytes;
+};
+int lstm_plan(int B, int H, LstmPlan &pl) {
+    MLVAE_REQUIRE(H % 32 == 0 && H >= 32 && H <= 768, MLVAE_ERR_UNSUPPORTED,
+                  "lstm: hidden size must be a multiple of 32 in [32, 768] (W_hh slice resident in tensor memory), got %d", H);
+    pl.G = H / kUnits;
+    const int sms = sm_count();
+    pl.NB = g_lstm_min_nb;       // batch rows per CTA: smallest of {16, 32, 64} with every CTA co-resident (1 CTA / SM)
+    while (pl.NB < 64 && (int64_t)pl.G * ((B + pl.NB - 1) / pl.NB) * 2 > sms) pl.NB *= 2;
+    pl.slices = (B + pl.NB - 1) / pl.NB;
+    MLVAE_REQUIRE((int64_t)pl.G * pl.slices * 2 <= sms, MLVAE_ERR_UNSUPPORTED,
+                  "lstm: batch %d x hidden %d needs %d co-resident CTAs (> %d SMs)", B, H, pl.G * pl.slices * 2, sms);
+    pl.smem = (size_t)pl.NB * H * 2 + (size_t)4 * pl.NB * 32 * 4;
+    pl.ll_bytes = (size_t)2 * 2 * pl.slices * pl.NB * (H / 2) * sizeof(uint2);
+    return MLVAE_OK;
+}
+}  // namespace
 
 extern "C" {
 
@@ -214,36 +292,41 @@ int mlvae_debug_set_profile_buffer(void *d_prof) {
     return MLVAE_OK;
 }
 
-// Scratch: one zeroed uint32 per (direction, batch slice).
-size_t mlvae_lstm_scratch_bytes(int B) { return sizeof(unsigned int) * 2 * (size_t)((B + 15) / 16) + 256; }
+// Debug / tuning: key 1 = number of MMA issuer warps of the LSTM kernels (1, 2 or 4).
+int mlvae_debug_set_option(int key, int value) {
+    if (key == 1) { g_lstm_issuers = value; return MLVAE_OK; }
+    if (key == 2 && (value == 16 || value == 32 || value == 64)) { g_lstm_min_nb = value; return MLVAE_OK; }
+    return fail(MLVAE_ERR_INVALID_ARG, "unknown debug option %d", key);
+}
+
+// Scratch: the {data, tag} exchange words, zeroed by every call.
+size_t mlvae_lstm_scratch_bytes(int B, int H) {
+    LstmPlan pl;
+    if (lstm_plan(B, H, pl) != MLVAE_OK) return 0;
+    return pl.ll_bytes + 256;
+}
 
 int mlvae_lstm_fwd(void *d_p, const void *d_whh, void *d_y, float *d_c, int B, int T, int H, int save_gates,
                    void *d_scratch, void *stream) {
     MLVAE_REQUIRE(d_p && d_whh && d_y && d_scratch, MLVAE_ERR_INVALID_ARG, "lstm_fwd: missing buffers");
-    MLVAE_REQUIRE(B > 0 && T > 0 && H > 0, MLVAE_ERR_INVALID_ARG, "lstm_fwd: bad sizes");
-    MLVAE_REQUIRE(H % 32 == 0 && H % 16 == 0 && H <= 704, MLVAE_ERR_UNSUPPORTED,
-                  "lstm_fwd: hidden size must be a multiple of 32 and <= 704 (W_hh slice resident in shared memory), got %d", H);
+    MLVAE_REQUIRE(B > 0 && T > 0 && H > 0 && T < (1 << 30), MLVAE_ERR_INVALID_ARG, "lstm_fwd: bad sizes");
+    LstmPlan pl;
+    if (int rc = lstm_plan(B, H, pl)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    const int G = H / kUnits;
-    const int sms = sm_count();
-    // batch rows per CTA: smallest of {16, 32, 64} that lets every CTA be co-resident (1 CTA / SM)
-    int NB = 16;
-    while (NB < 64 && (int64_t)G * ((B + NB - 1) / NB) * 2 > sms) NB *= 2;
-    const int slices = (B + NB - 1) / NB;
-    MLVAE_REQUIRE((int64_t)G * slices * 2 <= sms, MLVAE_ERR_UNSUPPORTED,
-                  "lstm_fwd: batch %d x hidden %d needs %d co-resident CTAs (> %d SMs)", B, H, G * slices * 2, sms);
-    const size_t smem = (size_t)kRows * H * 2 + (size_t)NB * H * 2 + (size_t)4 * NB * 32 * 4;
-    MLVAE_REQUIRE(smem <= 227 * 1024, MLVAE_ERR_UNSUPPORTED, "lstm_fwd: %zu bytes of shared memory needed", smem);
-    MLVAE_CHECK_CUDA(cudaMemsetAsync(d_scratch, 0, sizeof(unsigned int) * 2 * slices, st));
-    LstmFwdParams prm{(bf16 *)d_p, (const bf16 *)d_whh, (bf16 *)d_y, d_c, (unsigned int *)d_scratch, B, T, H, save_gates};
+    MLVAE_CHECK_CUDA(cudaMemsetAsync(d_scratch, 0, pl.ll_bytes, st));
+    LstmFwdParams prm{(bf16 *)d_p, (const bf16 *)d_whh, (bf16 *)d_y, d_c, (uint2 *)d_scratch, B, T, H, save_gates};
     void *args[] = {&prm};
-    dim3 grid(G, slices, 2), block(kLstmThreads);
+    dim3 grid(pl.G, pl.slices, 2), block(kLstmThreads);
     const void *fn = nullptr;
-    if (NB == 16) fn = (const void *)lstm_fwd_kernel<16>;
-    else if (NB == 32) fn = (const void *)lstm_fwd_kernel<32>;
-    else fn = (const void *)lstm_fwd_kernel<64>;
-    MLVAE_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MLVAE_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, grid, block, args, smem, st));
+    const int nch = (g_lstm_issuers == 1 || g_lstm_issuers == 2 || g_lstm_issuers == 4) ? g_lstm_issuers : 2;
+#define LSTM_PICK(NBV)                                                                    \
+    (nch == 1 ? (const void *)lstm_fwd_kernel<NBV, 1>                                     \
+              : nch == 2 ? (const void *)lstm_fwd_kernel<NBV, 2> : (const void *)lstm_fwd_kernel<NBV, 4>)
+    if (pl.NB == 16) fn = LSTM_PICK(16);
+    else if (pl.NB == 32) fn = LSTM_PICK(32);
+    else fn = (const void *)lstm_fwd_kernel<64, 2>;
+    MLVAE_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    MLVAE_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, grid, block, args, pl.smem, st));
     return MLVAE_OK;
 }
 
