@@ -196,6 +196,13 @@ int mlvae_debug_set_option(int key, int value);
 int mlvae_lstm_fwd(void *d_p, const void *d_whh, void *d_y, float *d_c, int B, int T, int H,
                    int save_gates, void *d_scratch, void *stream);
 
+/* Backward recurrence of the same layer.  d_gates: the (B,T,2,4H) buffer mlvae_lstm_fwd filled with
+ * activated gates (save_gates = 1); on return it holds the PRE-ACTIVATION gradients dA (bf16), from
+ * which the caller forms dW_ih = dA^T x, dW_hh = dA^T h_prev, db = sum dA, dx = dA W_ih (plain GEMMs).
+ * d_c: cell states from the forward pass; d_dy: (B,T,2H) bf16 gradient of the layer output. */
+int mlvae_lstm_bwd(void *d_gates, const float *d_c, const void *d_dy, const void *d_whh, int B, int T, int H,
+                   void *d_scratch, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -255,6 +255,226 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_fwd_kernel(LstmFwdParams
     if (warp == 0) tc::tmem_dealloc(tmem, tmem_cols);
 }
 
+
+// ======================================================================================
+// Backward recurrence.  Same groups / ownership as the forward pass.  Per step (reverse order):
+//   phase A  thread = (batch row j, unit): dh = dY + dh_rec; gate gradients -> pre-activation
+//            gradients da_{i,f,g,o}; written (bf16) over the saved gates in G (input of the weight /
+//            input GEMMs that follow) and into the K-major B-operand tile (NB x 128 gate rows)
+//   phase B  partial[jh, j] = sum_{r in my 128 gate rows} W_hh[r, jh] * da[j, r]   tcgen05.mma with the
+//            TRANSPOSED weight slice resident in TMEM (ceil(H/128) M-tiles x 64 columns)
+//   phase C  partials leave as {2 x bf16, tag} words addressed to the CTA that owns unit jh; every
+//            CTA sums the G partial slices it receives in fixed producer order (deterministic)
+// ======================================================================================
+struct LstmBwdParams {
+    bf16 *G;                 // (B, T, 2, 4H) in: activated gates from the forward pass; out: pre-activation grads
+    const float *C;          // (B, T, 2H) cell states from the forward pass
+    const bf16 *dY;          // (B, T, 2H) gradient of the layer output
+    const bf16 *Whh;         // (2, 4H, H)
+    uint2 *ll;               // [2 parity][groups][G consumers][G producers][NB/2][32] zeroed {data, tag} words
+    int B, T, H;
+};
+
+template <int NB, int NI>
+__global__ void __launch_bounds__(kLstmThreads, 1) lstm_bwd_kernel(LstmBwdParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t s_bar;
+    __shared__ uint32_t s_tmem;
+    static_assert(NB == 16, "backward kernel is instantiated for NB = 16");
+    const int H = p.H, T = p.T, B = p.B;
+    const int G = H / kUnits;
+    const int u = blockIdx.x, slice = blockIdx.y, d = blockIdx.z;
+    const int b0 = slice * NB;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q = warp & 3, part = warp >> 2;
+    constexpr int CPW = NB / 4;
+    const int tiles = (H + 127) / 128;
+    const int issuers = tiles < NI ? tiles : NI;
+
+    unsigned char *sDA = smem;                                           // NB x 128 bf16, K-major (4 KB)
+    float2 *s_part = reinterpret_cast<float2 *>(smem + NB * 128 * 2);    // [2 halves][NB/2][32]
+
+    const uint32_t dcol = (uint32_t)((tiles * 64 + 31) & ~31);
+    uint32_t tmem_cols = 32;
+    while (tmem_cols < dcol + (uint32_t)tiles * NB) tmem_cols <<= 1;
+    if (warp == 0) tc::tmem_alloc(&s_tmem, tmem_cols);
+    if (tid == 0) {
+        tc::mbar_init(&s_bar, issuers);
+        tc::fence_barrier_init();
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = s_tmem;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+
+    // ---- transposed weight slice -> TMEM: tile m, lane = jh - 128 m, K index r = gate*32 + unit ----
+    {
+        const unsigned short *W16 = reinterpret_cast<const unsigned short *>(p.Whh) + (size_t)d * 4 * H * H;
+        for (int m = part; m < tiles; m += 4) {
+            const int jh = 128 * m + 32 * q + lane;
+            for (int k16 = 0; k16 < 8; ++k16) {
+                uint32_t v[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    uint32_t lo = 0, hi = 0;
+                    if (jh < H) {
+                        const int r0 = k16 * 16 + 2 * e, r1 = r0 + 1;
+                        lo = W16[((size_t)(r0 >> 5) * H + u * kUnits + (r0 & 31)) * H + jh];
+                        hi = W16[((size_t)(r1 >> 5) * H + u * kUnits + (r1 & 31)) * H + jh];
+                    }
+                    v[e] = lo | (hi << 16);
+                }
+                tc::tmem_st8(tmem + lane_base + m * 64 + k16 * 8, v);
+            }
+        }
+        tc::tmem_st_wait();
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+
+    const uint32_t idesc = tc::idesc_bf16_f32(128, NB);
+    const int groups = 2 * gridDim.y;
+    const int group = d * gridDim.y + slice;
+    const size_t ll_words = (size_t)G * G * (NB / 2) * 32;
+    const int c_half = (G + 1) / 2;
+
+    // phase-A identity of this thread
+    const int j = warp, unit = lane;
+    const int b = min(b0 + j, B - 1);                 // rows past B are clamped for loads, never stored
+    const bool row_ok = (b0 + j) < B;
+    const size_t g_row = (size_t)2 * 4 * H;
+    const unsigned short *G16 = reinterpret_cast<const unsigned short *>(p.G);
+    const unsigned short *dY16 = reinterpret_cast<const unsigned short *>(p.dY);
+    auto g_index = [&](int t, int gate) { return ((size_t)b * T + t) * g_row + (size_t)d * 4 * H + (size_t)gate * H + u * kUnits + unit; };
+    auto y_index = [&](int t) { return ((size_t)b * T + t) * (2 * H) + d * H + u * kUnits + unit; };
+
+    float dc_carry = 0.f;
+    // raw prefetch for the first step
+    int t = d ? 0 : (T - 1);
+    unsigned short rg[4], rdy;
+    float rc, rcp;
+    {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) rg[g] = G16[g_index(t, g)];
+        rdy = dY16[y_index(t)];
+        rc = p.C[y_index(t)];
+        const int tp = d ? (t + 1) : (t - 1);
+        rcp = (tp >= 0 && tp < T) ? p.C[y_index(tp)] : 0.f;
+    }
+    long long *prof = (g_prof && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? g_prof : nullptr;
+    long long tprev = clock64();
+
+    for (int step = 0; step < T; ++step) {
+        t = d ? step : (T - 1 - step);
+        float dh_rec = 0.f;
+        if (step > 0) {
+            // ---- phase C (consumer side): sum the partial slices addressed to this CTA ----
+            const uint2 *src = p.ll + ((size_t)(step & 1) * groups + group) * ll_words + (size_t)u * G * (NB / 2) * 32;
+            const int jp = warp & 7, half = warp >> 3;
+            const int c_lo = half * c_half, c_hi = min(G, c_lo + c_half);
+            float sx = 0.f, sy = 0.f;
+            uint2 w[8];
+#pragma unroll
+            for (int n = 0; n < 8; ++n)
+                if (c_lo + n < c_hi) w[n] = ld_volatile_u2(src + ((size_t)(c_lo + n) * (NB / 2) + jp) * 32 + lane);
+#pragma unroll
+            for (int n = 0; n < 8; ++n) {
+                if (c_lo + n < c_hi) {
+                    const uint2 *a = src + ((size_t)(c_lo + n) * (NB / 2) + jp) * 32 + lane;
+                    while (w[n].y != (uint32_t)step) w[n] = ld_volatile_u2(a);
+                    sx += __uint_as_float(w[n].x << 16);
+                    sy += __uint_as_float(w[n].x & 0xffff0000u);
+                }
+            }
+            for (int c = c_lo + 8; c < c_hi; ++c) {               // G > 16 (H > 512)
+                const uint2 *a = src + ((size_t)c * (NB / 2) + jp) * 32 + lane;
+                uint2 x = ld_volatile_u2(a);
+                while (x.y != (uint32_t)step) x = ld_volatile_u2(a);
+                sx += __uint_as_float(x.x << 16);
+                sy += __uint_as_float(x.x & 0xffff0000u);
+            }
+            s_part[(half * (NB / 2) + jp) * 32 + lane] = make_float2(sx, sy);
+            __syncthreads();
+            const float2 p0 = s_part[(0 * (NB / 2) + (j >> 1)) * 32 + unit], p1 = s_part[(1 * (NB / 2) + (j >> 1)) * 32 + unit];
+            dh_rec = (j & 1) ? (p0.y + p1.y) : (p0.x + p1.x);
+        }
+        PROF_MARK(0);                                   // partial gather + reduce
+        // ---- phase A: gate gradients ----
+        const float gi = __uint_as_float((uint32_t)rg[0] << 16), gf = __uint_as_float((uint32_t)rg[1] << 16);
+        const float gg = __uint_as_float((uint32_t)rg[2] << 16), go = __uint_as_float((uint32_t)rg[3] << 16);
+        const float dh = __uint_as_float((uint32_t)rdy << 16) + dh_rec;
+        const float tc_ = tanh_f(rc);
+        const float dc = dc_carry + dh * go * (1.f - tc_ * tc_);
+        const float da_i = dc * gg * gi * (1.f - gi);
+        const float da_f = dc * rcp * gf * (1.f - gf);
+        const float da_g = dc * gi * (1.f - gg * gg);
+        const float da_o = dh * tc_ * go * (1.f - go);
+        dc_carry = dc * gf;
+        const float da[4] = {da_i, da_f, da_g, da_o};
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const bf16 v = __float2bfloat16_rn(da[g]);
+            *reinterpret_cast<bf16 *>(sDA + tc::kmajor_off(j, g * 32 + unit, 128)) = v;
+            if (row_ok) p.G[g_index(t, g)] = v;
+        }
+        if (step + 1 < T) {                              // raw prefetch for the next step
+            const int tn = d ? (t + 1) : (t - 1);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) rg[g] = G16[g_index(tn, g)];
+            rdy = dY16[y_index(tn)];
+            rc = p.C[y_index(tn)];
+            const int tp = d ? (tn + 1) : (tn - 1);
+            rcp = (tp >= 0 && tp < T) ? p.C[y_index(tp)] : 0.f;
+        }
+        if (step + 1 == T) break;                        // dh_rec of the last step is never used
+        tc::fence_proxy_async();
+        tc::fence_before_sync();
+        __syncthreads();
+        PROF_MARK(1);                                   // gate gradients
+        // ---- phase B: partial[jh, j] over my 128 gate rows ----
+        if (warp < issuers) {
+            if (tc::elect_one()) {
+                tc::fence_after_sync();
+                const uint64_t b_desc0 = tc::smem_desc(tc::smem_u32(sDA), 128, 2048);
+                for (int m = warp; m < tiles; m += issuers) {
+#pragma unroll
+                    for (int k16 = 0; k16 < 8; ++k16)
+                        tc::mma_bf16_ts(tmem + dcol + m * NB, tmem + m * 64 + k16 * 8, b_desc0 + (uint64_t)(k16 * 16), idesc, k16 > 0);
+                }
+                tc::mma_commit(&s_bar);
+            }
+            __syncwarp();
+        }
+        tc::mbar_wait(&s_bar, step & 1);
+        tc::fence_after_sync();
+        PROF_MARK(2);                                   // MMA
+        // ---- phase C (producer side): ship partials to the owners of units jh ----
+        uint2 *dst = p.ll + ((size_t)((step + 1) & 1) * groups + group) * ll_words;
+        for (int m = 0; m < tiles; ++m) {
+            uint32_t v[CPW];
+            tc::tmem_ld<CPW>(tmem + lane_base + dcol + m * NB + part * CPW, v);
+            tc::tmem_ld_wait();
+            const int owner = 4 * m + q;                 // CTA that owns unit jh = 128 m + 32 q + lane
+            if (owner < G) {
+#pragma unroll
+                for (int e = 0; e < CPW / 2; ++e) {
+                    const __nv_bfloat162 pk = __floats2bfloat162_rn(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]));
+                    const int jp = part * (CPW / 2) + e;
+                    st_volatile_u2(dst + (((size_t)owner * G + u) * (NB / 2) + jp) * 32 + lane,
+                                   make_uint2(*reinterpret_cast<const uint32_t *>(&pk), (uint32_t)(step + 1)));
+                }
+            }
+        }
+        tc::fence_before_sync();
+        PROF_MARK(3);                                   // partial scatter
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, tmem_cols);
+}
+
 }  // namespace
 }  // namespace mlvae
 
@@ -303,7 +523,8 @@ int mlvae_debug_set_option(int key, int value) {
 size_t mlvae_lstm_scratch_bytes(int B, int H) {
     LstmPlan pl;
     if (lstm_plan(B, H, pl) != MLVAE_OK) return 0;
-    return pl.ll_bytes + 256;
+    const size_t bwd = (size_t)2 * 2 * ((B + 15) / 16) * pl.G * pl.G * 8 * 32 * sizeof(uint2);
+    return (pl.ll_bytes > bwd ? pl.ll_bytes : bwd) + 256;
 }
 
 int mlvae_lstm_fwd(void *d_p, const void *d_whh, void *d_y, float *d_c, int B, int T, int H, int save_gates,
@@ -327,6 +548,31 @@ int mlvae_lstm_fwd(void *d_p, const void *d_whh, void *d_y, float *d_c, int B, i
     else fn = (const void *)lstm_fwd_kernel<64, 2>;
     MLVAE_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
     MLVAE_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, grid, block, args, pl.smem, st));
+    return MLVAE_OK;
+}
+
+
+int mlvae_lstm_bwd(void *d_gates, const float *d_c, const void *d_dy, const void *d_whh, int B, int T, int H,
+                   void *d_scratch, void *stream) {
+    MLVAE_REQUIRE(d_gates && d_c && d_dy && d_whh && d_scratch, MLVAE_ERR_INVALID_ARG, "lstm_bwd: missing buffers");
+    MLVAE_REQUIRE(B > 0 && T > 0 && H > 0 && T < (1 << 30), MLVAE_ERR_INVALID_ARG, "lstm_bwd: bad sizes");
+    LstmPlan pl;
+    if (int rc = lstm_plan(B, H, pl)) return rc;
+    MLVAE_REQUIRE(pl.NB == 16 || (int64_t)pl.G * ((B + 15) / 16) * 2 <= sm_count(), MLVAE_ERR_UNSUPPORTED,
+                  "lstm_bwd: batch %d x hidden %d does not fit one 16-row slice per CTA", B, H);
+    const int slices = (B + 15) / 16;
+    MLVAE_REQUIRE((int64_t)pl.G * slices * 2 <= sm_count(), MLVAE_ERR_UNSUPPORTED,
+                  "lstm_bwd: batch %d x hidden %d needs %d co-resident CTAs", B, H, pl.G * slices * 2);
+    const size_t ll_bytes = (size_t)2 * 2 * slices * pl.G * pl.G * 8 * 32 * sizeof(uint2);
+    cudaStream_t st = (cudaStream_t)stream;
+    MLVAE_CHECK_CUDA(cudaMemsetAsync(d_scratch, 0, ll_bytes, st));
+    LstmBwdParams prm{(bf16 *)d_gates, d_c, (const bf16 *)d_dy, (const bf16 *)d_whh, (uint2 *)d_scratch, B, T, H};
+    void *args[] = {&prm};
+    dim3 grid(pl.G, slices, 2), block(kLstmThreads);
+    const void *fn = (g_lstm_issuers == 1) ? (const void *)lstm_bwd_kernel<16, 1>
+                     : (g_lstm_issuers == 4) ? (const void *)lstm_bwd_kernel<16, 4> : (const void *)lstm_bwd_kernel<16, 2>;
+    const size_t smem = 16 * 128 * 2 + 2 * 8 * 32 * sizeof(float2);
+    MLVAE_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, grid, block, args, smem, st));
     return MLVAE_OK;
 }
 

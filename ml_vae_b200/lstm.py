@@ -1,0 +1,82 @@
+"""Bidirectional LSTM layer on the persistent tcgen05 kernels (csrc/lstm.cu).
+
+Replaces, for bf16 activations, the cuDNN path behind ``nn.LSTM(..., bidirectional=True,
+batch_first=True)`` that the reference's Decoder uses (modules/decoder.py:14-15,22).  The big,
+time-parallel GEMMs (input projection, dX, dW_ih, dW_hh) are library GEMMs through torch; the
+sequential part -- T dependent steps per direction -- is ONE cooperative kernel per pass instead
+of 2 x T cuDNN launches.  Gate order and parameter layout are torch's (i, f, g, o).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib as L
+
+_scratch = {}
+
+
+def supported(x: torch.Tensor, hidden: int) -> bool:
+    return x.is_cuda and x.dtype == torch.bfloat16 and hidden % 32 == 0 and 32 <= hidden <= 768 \
+        and L.lib().mlvae_lstm_scratch_bytes(x.shape[0], hidden) > 0
+
+
+def _get_scratch(B, H, device):
+    need = L.lib().mlvae_lstm_scratch_bytes(B, H)
+    if need == 0:
+        raise L.MlvaeError(f"persistent LSTM does not support batch {B} x hidden {H}: {L.lib().mlvae_last_error().decode()}")
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    buf = _scratch.get(key)
+    if buf is None or buf.numel() < need:
+        buf = torch.empty(need, dtype=torch.uint8, device=device)
+        _scratch[key] = buf
+    return buf
+
+
+class _BiLSTMLayer(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w_ih, w_hh, bias, training):
+        """x (B,T,In) bf16; w_ih (8H,In) bf16 [fwd rows then reverse rows]; w_hh (2,4H,H) bf16;
+        bias (8H,) bf16 = b_ih + b_hh of both directions -> y (B,T,2H) bf16."""
+        B, T, In = x.shape
+        H = w_hh.shape[2]
+        x2 = x.reshape(B * T, In)
+        P = torch.addmm(bias, x2, w_ih.t()).view(B, T, 2, 4 * H)            # library GEMM (time-parallel)
+        y = torch.empty(B, T, 2 * H, dtype=torch.bfloat16, device=x.device)
+        c = torch.empty(B, T, 2 * H, dtype=torch.float32, device=x.device) if training else None
+        L.check(L.lib().mlvae_lstm_fwd(L.ptr(P), L.ptr(w_hh), L.ptr(y), L.ptr(c), B, T, H, int(training),
+                                       L.ptr(_get_scratch(B, H, x.device)), L.stream_ptr()), "mlvae_lstm_fwd")
+        if training:
+            ctx.save_for_backward(x, w_ih, w_hh, P, c, y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w_ih, w_hh, gates, c, y = ctx.saved_tensors
+        B, T, In = x.shape
+        H = w_hh.shape[2]
+        dy = dy.contiguous().to(torch.bfloat16)
+        L.check(L.lib().mlvae_lstm_bwd(L.ptr(gates), L.ptr(c), L.ptr(dy), L.ptr(w_hh), B, T, H,
+                                       L.ptr(_get_scratch(B, H, x.device)), L.stream_ptr()), "mlvae_lstm_bwd")
+        dA = gates                                                         # now pre-activation gradients (B,T,2,4H)
+        dA2 = dA.view(B * T, 8 * H)
+        x2 = x.reshape(B * T, In)
+        dx = (dA2 @ w_ih).view(B, T, In)
+        dw_ih = dA2.t() @ x2
+        db = dA2.sum(0, dtype=torch.float32)
+        dw_hh = torch.empty_like(w_hh)
+        if T > 1:
+            # h_{t-1} in each direction's own order: forward uses y[:, t-1, :H], reverse uses y[:, t+1, H:]
+            dw_hh[0] = dA[:, 1:, 0].reshape(-1, 4 * H).t() @ y[:, :-1, :H].reshape(-1, H)
+            dw_hh[1] = dA[:, :-1, 1].reshape(-1, 4 * H).t() @ y[:, 1:, H:].reshape(-1, H)
+        else:
+            dw_hh.zero_()
+        return dx, dw_ih, dw_hh, db.to(torch.bfloat16), None
+
+
+def bilstm_layer(x, w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r, training: bool):
+    """One bidirectional layer with torch's per-direction parameters (float32 masters are cast here)."""
+    bf = torch.bfloat16
+    w_ih = torch.cat([w_ih_f, w_ih_r], 0).to(bf)
+    w_hh = torch.stack([w_hh_f, w_hh_r], 0).to(bf)
+    bias = torch.cat([b_ih_f + b_hh_f, b_ih_r + b_hh_r], 0).to(bf)
+    return _BiLSTMLayer.apply(x.contiguous(), w_ih, w_hh, bias, training)

@@ -15,7 +15,7 @@ from __future__ import annotations
 import torch
 from torch import nn
 
-from .. import ops
+from .. import lstm, ops
 from ..dense import linear_chain
 from ._params import attach, torch_default_linear, torch_default_lstm
 
@@ -31,6 +31,7 @@ class Decoder(nn.Module):
         self.fc_sizes = [int(s) for s in fc_sizes]
         self.loss_type = loss_type
         self.materialize_loss = materialize_loss
+        self.use_persistent_lstm = True
         self._rnn_names = []
         for name, p in torch_default_lstm(self.input_size, self.hidden, self.num_layers):
             attach(self, f"rnn.{name}", p)
@@ -47,7 +48,18 @@ class Decoder(nn.Module):
         return [blocks[str(2 * i)].weight for i in range(n)], [blocks[str(2 * i)].bias for i in range(n)]
 
     def run_rnn(self, x):
-        """decoder.py:14-15,22: 2-layer bidirectional LSTM, batch_first, inter-layer dropout."""
+        """decoder.py:14-15,22: 2-layer bidirectional LSTM, batch_first, inter-layer dropout.
+        bf16 activations run on the persistent tcgen05 recurrence (csrc/lstm.cu); float32 (and hidden
+        sizes that are not a multiple of 32) go through cuDNN."""
+        if self.use_persistent_lstm and lstm.supported(x, self.hidden):
+            need_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.rnn.parameters()))
+            for layer in range(self.num_layers):
+                ps = [getattr(self.rnn, f"{kind}_l{layer}{sfx}") for sfx in ("", "_reverse")
+                      for kind in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")]
+                x = lstm.bilstm_layer(x, *ps, training=need_grad)
+                if self.rnn_dropout > 0 and self.training and layer + 1 < self.num_layers:
+                    x = torch.nn.functional.dropout(x, self.rnn_dropout, True)
+            return x
         flat = [getattr(self.rnn, n).to(x.dtype) for n in self._rnn_names]
         z = x.new_zeros(2 * self.num_layers, x.shape[0], self.hidden)
         out, _, _ = torch._VF.lstm(x, (z, z), flat, True, self.num_layers, self.rnn_dropout, self.training, True, True)

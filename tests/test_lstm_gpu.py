@@ -1,0 +1,87 @@
+"""GPU parity of the tcgen05 building blocks and the persistent LSTM (csrc/gemm_chain.cu, csrc/lstm.cu)
+against torch: single MMA tiles bit-close to an fp32 matmul of the same bf16 inputs; the LSTM layer
+forward and every gradient within the bf16 tolerance (1e-2 rel) of torch.nn.LSTM in float32 on the
+same bf16-rounded weights and inputs."""
+import pytest
+import torch
+
+from _util import BF16_RTOL, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("N,K,ts", [(16, 16, 0), (64, 64, 0), (80, 64, 0), (256, 256, 0), (144, 320, 0),
+                                     (16, 16, 1), (32, 512, 1), (64, 256, 1)])
+def test_tcgen05_tile_matches_matmul(cuda, N, K, ts):
+    from ml_vae_b200 import _lib as L
+    g = torch.Generator().manual_seed(N * 1000 + K)
+    a = torch.randn(128, K, generator=g).bfloat16().to(cuda)
+    b = torch.randn(N, K, generator=g).bfloat16().to(cuda)
+    d = torch.full((128, N), float("nan"), device=cuda)
+    L.check(L.lib().mlvae_tc05_selftest(L.ptr(a), L.ptr(b), L.ptr(d), N, K, ts, L.stream_ptr()), "selftest")
+    ref = a.float() @ b.float().t()
+    assert rel_err(d, ref) < 2e-6
+
+
+@pytest.mark.parametrize("B,T,In,H", [(4, 6, 16, 32), (16, 20, 24, 64), (20, 33, 64, 128), (7, 40, 48, 256), (64, 60, 64, 512)])
+def test_persistent_lstm_layer_fwd_bwd_vs_torch(cuda, B, T, In, H):
+    from ml_vae_b200.lstm import bilstm_layer
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(B + T + H)
+    ref = torch.nn.LSTM(In, H, 1, bidirectional=True, batch_first=True).to(cuda)
+    with torch.no_grad():
+        for p in ref.parameters():
+            p.copy_(p.bfloat16().float())
+    x = torch.randn(B, T, In, device=cuda).bfloat16()
+    gy = torch.randn(B, T, 2 * H, device=cuda).bfloat16()
+    xr = x.float().requires_grad_(True)
+    yr, _ = ref(xr)
+    (yr * gy.float()).sum().backward()
+    names = [f"{k}_l0{s}" for s in ("", "_reverse") for k in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")]
+    ps = [getattr(ref, n).detach().clone().requires_grad_(True) for n in names]
+    xm = x.clone().requires_grad_(True)
+    y = bilstm_layer(xm, *ps, training=True)
+    (y.float() * gy.float()).sum().backward()
+    assert rel_err(y, yr) < BF16_RTOL
+    assert rel_err(xm.grad, xr.grad) < BF16_RTOL
+    for n, p in zip(names, ps):
+        assert rel_err(p.grad, getattr(ref, n).grad) < BF16_RTOL, n
+    # inference path (no saved state) gives the same output
+    with torch.no_grad():
+        y2 = bilstm_layer(x, *[p.detach() for p in ps], training=False)
+    assert torch.equal(y2, y.detach())
+
+
+def test_decoder_uses_persistent_lstm_in_bf16_and_matches_cudnn(cuda):
+    """Whole decoder (2 x biLSTM + heads + fused NLL) in bf16 on the persistent kernels, against the float32
+    cuDNN path as the reference; it must stay within 3e-2 (or twice the error of cuDNN own bf16 path) on loss and weight gradients."""
+    from ml_vae_b200.modules import Decoder
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(0)
+    dec = Decoder(64, 128, 2, 0.0, [256, 64, 64, 80]).to(cuda)
+    z = torch.randn(6, 50, 64, device=cuda).bfloat16()
+    tgt = torch.randn(6, 50, 80, device=cuda).bfloat16()
+    lens = torch.tensor([1.0, 0.9, 0.7, 0.5, 1.0, 0.3], device=cuda)
+
+    def run(persistent, dtype):
+        dec.use_persistent_lstm = persistent
+        dec.zero_grad()
+        o = dec(z.to(dtype), tgt.to(dtype), lens=lens)
+        o["recon_loss"].backward()
+        return (o["recon_loss"].detach().float(), dec.rnn.weight_hh_l1.grad.clone(), dec.rnn.weight_ih_l0.grad.clone(),
+                dec.mean_fc.blocks._modules["0"].weight.grad.clone())
+
+    ref = run(False, torch.float32)
+    ours = run(True, torch.bfloat16)
+    lib = run(False, torch.bfloat16)
+    for a, b, r, name in zip(ours, lib, ref, ["loss", "dW_hh_l1", "dW_ih_l0", "dW_head"]):
+        e_ours, e_lib = rel_err(a, r), rel_err(b, r)
+        assert e_ours <= max(3e-2, 2.0 * e_lib), (name, e_ours, e_lib)
+
+
+def test_unsupported_hidden_size_is_refused(cuda):
+    from ml_vae_b200 import _lib as L
+    assert L.lib().mlvae_lstm_scratch_bytes(8, 48) == 0
+    assert b"multiple of 32" in L.lib().mlvae_last_error()
