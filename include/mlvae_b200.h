@@ -180,7 +180,7 @@ int mlvae_tc05_selftest(const void *d_a, const void *d_b, float *d_d, int N, int
  * bidirectional); one layer per call).  The input projection x W_ih^T + b_ih + b_hh for all
  * timesteps is a plain GEMM done by the caller into d_p; this entry point walks the T
  * recurrent steps of BOTH directions in one cooperative launch (tcgen05 + TMEM, W_hh
- * resident in shared memory).  bf16 only; H % 32 == 0, H <= 704.
+ * resident in shared memory).  bf16 only; H % 32 == 0, H <= 512.
  *   d_p   (B, T, 2, 4H) bf16  gate pre-activations, torch gate order i,f,g,o; when
  *                             save_gates != 0 it is overwritten with the activated gates
  *   d_whh (2, 4H, H)    bf16  weight_hh_l{k}, weight_hh_l{k}_reverse

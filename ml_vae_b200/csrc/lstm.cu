@@ -31,8 +31,8 @@ constexpr int kRows = 4 * kUnits;     // gate rows per CTA == MMA M
 constexpr int kLstmThreads = 512;
 constexpr int kLstmWarps = kLstmThreads / 32;
 
-__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + __expf(-x)); }
-__device__ __forceinline__ float tanh_f(float x) { return 2.f / (1.f + __expf(-2.f * x)) - 1.f; }
+__device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float tanh_f(float x) { return __fdividef(2.f, 1.f + __expf(-2.f * x)) - 1.f; }
 
 __device__ __forceinline__ uint2 ld_volatile_u2(const uint2 *p) {
     uint2 v;
@@ -70,20 +70,26 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_fwd_kernel(LstmFwdParams
     const int d = blockIdx.z;                     // direction
     const int b0 = slice * NB;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int q = warp & 3;                       // TMEM lane group of this warp == gate (i, f, g, o)
-    const int part = warp >> 2;                   // which quarter of the columns this warp handles
-    constexpr int CPW = NB / 4;                   // accumulator columns (batch rows) per warp
-    constexpr int IPT = NB * kUnits / kLstmThreads;   // (batch row, unit) cell items per thread
+    const int q = warp & 3;                       // TMEM lane group of this warp
+    const int part = warp >> 2;                   // which quarter of the accumulator columns (batch rows)
+    constexpr int CPW = NB / 4;                   // batch rows per warp
+    static_assert(CPW == 4, "the quad transpose below assumes 4 batch rows per warp (NB == 16)");
+    // Gate rows are interleaved so that the 4 gates of a unit sit in 4 adjacent TMEM lanes:
+    //   CTA row r = unit_local * 4 + gate  ->  lane = r % 32 of group q = r / 32
+    // After the MMA a quad of lanes holds {i, f, g, o} x 4 batch rows of one unit; a 4 x 4 shuffle transpose
+    // gives every lane all four gates of ONE (unit, batch row): no shared-memory round trip, no block barrier
+    // between the non-linearity and the cell update.
+    const int gate = lane & 3;
+    const int unit_local = 8 * q + (lane >> 2);
     // NCH issuer warps, each feeding its own accumulator tile with the K steps k = w (mod NCH): issuing the
     // H/16 small MMAs from one thread is instruction-issue bound (descriptor arithmetic on the uniform
     // datapath), while more tiles cost TMEM read bandwidth in the epilogue (64 B/cycle).
 
     unsigned char *sH = smem;                                               // NB x H bf16, K-major
-    float *s_act = reinterpret_cast<float *>(smem + (size_t)NB * H * 2);    // [4][NB][32]
 
     const uint32_t dcol = (uint32_t)((H / 2 + 31) & ~31);                   // accumulator columns start
     uint32_t tmem_cols = 32;
-    while (tmem_cols < dcol + 128) tmem_cols <<= 1;
+    while (tmem_cols < dcol + NCH * NB) tmem_cols <<= 1;
     if (warp == 0) tc::tmem_alloc(&s_tmem, tmem_cols);
     if (tid == 0) {
         tc::mbar_init(&s_bar, NCH);
@@ -95,9 +101,9 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_fwd_kernel(LstmFwdParams
     const uint32_t tmem = s_tmem;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
 
-    // ---- resident weights: row (gate q, unit lane) of W_hh[d] -> TMEM lane 32q+lane, columns k/2 ----
+    // ---- resident weights: W_hh[d][gate*H + u*32 + unit_local][:] -> this thread's TMEM lane, columns k/2 ----
     {
-        const bf16 *wrow = p.Whh + ((size_t)d * 4 * H + (size_t)q * H + u * kUnits + lane) * H;
+        const bf16 *wrow = p.Whh + ((size_t)d * 4 * H + (size_t)gate * H + u * kUnits + unit_local) * H;
         for (int k16 = part; k16 < H / 16; k16 += 4) {
             const uint4 lo = __ldg(reinterpret_cast<const uint4 *>(wrow + k16 * 16));
             const uint4 hi = __ldg(reinterpret_cast<const uint4 *>(wrow + k16 * 16 + 8));
@@ -117,58 +123,68 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_fwd_kernel(LstmFwdParams
     const size_t ll_words = (size_t)NB * (H / 2);
     const int n_words = NB * (H / 2);
 
-    float c_state[IPT];
+    // ---- per-thread constant addressing, hoisted out of the time loop ----
+    const int t_first = d ? (T - 1) : 0;
+    const ptrdiff_t p_step = (ptrdiff_t)(d ? -1 : 1) * 2 * 4 * H;           // P elements per time step
+    const ptrdiff_t y_step = (ptrdiff_t)(d ? -1 : 1) * 2 * H;
+    unsigned short *pP[CPW];                                                 // (gate, unit) of batch rows part*4 + i
+    bool row_ok[CPW];
 #pragma unroll
-    for (int j = 0; j < IPT; ++j) c_state[j] = 0.f;
-
-    const size_t p_row = (size_t)2 * 4 * H;                              // elements per (b, t) in P
-    const size_t gate_col = (size_t)d * 4 * H + (size_t)q * H + u * kUnits + lane;
-    auto p_index = [&](int j, int t) { return ((size_t)(b0 + j) * T + t) * p_row + gate_col; };
-
-    // input-projection terms are prefetched one step ahead as RAW bf16 bits: converting at load time
-    // would stall the warp on the DRAM latency inside the step
-    const unsigned short *P16 = reinterpret_cast<const unsigned short *>(p.P);
-    unsigned short pre_raw[CPW];
-    {
-        const int t0 = d ? (T - 1) : 0;
-#pragma unroll
-        for (int i = 0; i < CPW; ++i) {
-            const int j = part * CPW + i;
-            pre_raw[i] = P16[p_index(min(j, B - 1 - b0), t0)];      // rows past B: clamp (their results are never stored)
-        }
+    for (int i = 0; i < CPW; ++i) {
+        const int b = b0 + part * CPW + i;
+        row_ok[i] = b < B;
+        pP[i] = reinterpret_cast<unsigned short *>(p.P) +
+                ((size_t)min(b, B - 1) * T + t_first) * (2 * 4 * H) + (size_t)d * 4 * H + (size_t)gate * H + u * kUnits + unit_local;
     }
+    const int my_row = part * CPW + gate;                                    // batch row this lane owns after the transpose
+    const bool my_ok = (b0 + my_row) < B;
+    const size_t y_off = ((size_t)min(b0 + my_row, B - 1) * T + t_first) * (2 * H) + d * H + u * kUnits + unit_local;
+    bf16 *pY = p.Y + y_off;
+    float *pC = p.C ? p.C + y_off : nullptr;
+    const size_t ll_mine = (size_t)my_row * (H / 2) + (u * kUnits + unit_local) / 2;
+    constexpr int WB = 8;                                                    // exchange words per thread per round
+    // word i = n * 512 + tid -> (batch row j, unit pair kw); its K-major byte offset is computed once (H <= 512
+    // guarantees NB * H/2 <= 512 * WB words)
+    uint32_t soff[WB];
+#pragma unroll
+    for (int n = 0; n < WB; ++n) {
+        const int i = n * kLstmThreads + tid;
+        const int j = i / (H / 2), kw = i - j * (H / 2);
+        soff[n] = tc::kmajor_off(j < NB ? j : 0, 2 * kw, H);
+    }
+    float c_state = 0.f;
+
+    // input-projection terms are prefetched one step ahead as RAW bf16 bits (converting at load time would
+    // stall the warp on the DRAM latency inside the step)
+    unsigned short pre_raw[CPW];
+#pragma unroll
+    for (int i = 0; i < CPW; ++i) pre_raw[i] = *pP[i];
+
     long long *prof = (g_prof && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? g_prof : nullptr;
     long long tprev = clock64();
 
     for (int step = 0; step < T; ++step) {
-        const int t = d ? (T - 1 - step) : step;
         float acc[CPW];
         if (step > 0) {
-            // ---- gather h_{t_prev}: poll the {data, tag} words of this group, tag == step ----
+            // ---- gather h_{t_prev}: the {data, tag} words of this group, tag == step ----
             const uint2 *src = p.ll + ((size_t)(step & 1) * groups + group) * ll_words;
-            constexpr int WB = 8;                        // words per thread per round
-            for (int i0 = tid; i0 < n_words; i0 += kLstmThreads * WB) {
+            {
+                const uint2 *wsrc = src + tid;
                 uint2 w[WB];
-                // spin on ONE word per thread (light polling traffic), then fetch the rest and re-check
-                w[0] = ld_volatile_u2(src + i0);
-                while (w[0].y != (uint32_t)step) w[0] = ld_volatile_u2(src + i0);
-#pragma unroll
-                for (int n = 1; n < WB; ++n) {
-                    const int i = i0 + n * kLstmThreads;
-                    if (i < n_words) w[n] = ld_volatile_u2(src + i);
+                // spin on ONE word per thread (polling all of them floods L2 and delays the producers' stores:
+                // measured 5.7k vs 3.7k cycles), then fetch the rest and re-check each
+                if (tid < n_words) {
+                    w[0] = ld_volatile_u2(wsrc);
+                    while (w[0].y != (uint32_t)step) w[0] = ld_volatile_u2(wsrc);
                 }
 #pragma unroll
-                for (int n = 1; n < WB; ++n) {
-                    const int i = i0 + n * kLstmThreads;
-                    if (i < n_words)
-                        while (w[n].y != (uint32_t)step) w[n] = ld_volatile_u2(src + i);
-                }
+                for (int n = 1; n < WB; ++n)
+                    if (n * kLstmThreads + tid < n_words) w[n] = ld_volatile_u2(wsrc + n * kLstmThreads);
 #pragma unroll
                 for (int n = 0; n < WB; ++n) {
-                    const int i = i0 + n * kLstmThreads;
-                    if (i >= n_words) continue;
-                    const int j = i / (H / 2), kw = i - j * (H / 2);
-                    *reinterpret_cast<uint32_t *>(sH + tc::kmajor_off(j, 2 * kw, H)) = w[n].x;
+                    if (n * kLstmThreads + tid >= n_words) continue;
+                    while (w[n].y != (uint32_t)step) w[n] = ld_volatile_u2(wsrc + n * kLstmThreads);
+                    *reinterpret_cast<uint32_t *>(sH + soff[n]) = w[n].x;
                 }
             }
             tc::fence_proxy_async();
@@ -202,59 +218,61 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_fwd_kernel(LstmFwdParams
                     if (c < H / 16) a += __uint_as_float(v[c][i]);
                 acc[i] = a;
             }
+            tc::fence_before_sync();                     // orders these TMEM reads before the next step's MMAs
         } else {
 #pragma unroll
             for (int i = 0; i < CPW; ++i) acc[i] = 0.f;      // h_0 = 0
         }
-        // ---- gate non-linearity: warp group q = 0: i, 1: f, 2: g (tanh), 3: o ----
+        // ---- gate non-linearity, divergence free: sigma(x) for i, f, o and tanh(x) = 2 sigma(2x) - 1 for g ----
+        const float kx = (gate == 2) ? 2.f : 1.f;
+        float a[CPW];
 #pragma unroll
         for (int i = 0; i < CPW; ++i) {
-            const int j = part * CPW + i;
             const float x = acc[i] + __uint_as_float((uint32_t)pre_raw[i] << 16);
-            const float a = (q == 2) ? tanh_f(x) : sigmoid_f(x);
-            s_act[(q * NB + j) * 32 + lane] = a;
-            if (p.save && b0 + j < B) p.P[p_index(j, t)] = __float2bfloat16_rn(a);
+            const float sg = __fdividef(1.f, 1.f + __expf(-kx * x));
+            a[i] = (gate == 2) ? (2.f * sg - 1.f) : sg;
+            if (p.save && row_ok[i]) *pP[i] = __bfloat16_as_ushort(__float2bfloat16_rn(a[i]));
+            pP[i] += p_step;
         }
         if (step + 1 < T) {                              // prefetch next step's input projection
-            const int tn = d ? (t - 1) : (t + 1);
 #pragma unroll
-            for (int i = 0; i < CPW; ++i) {
-                const int j = part * CPW + i;
-                pre_raw[i] = P16[p_index(min(j, B - 1 - b0), tn)];
-            }
+            for (int i = 0; i < CPW; ++i) pre_raw[i] = *pP[i];
         }
-        tc::fence_before_sync();
-        __syncthreads();
-        PROF_MARK(2);                                   // tmem load + activation
-        // ---- cell update + publish: thread = (batch row j, unit = lane) ----
-        uint2 *dst = p.ll + ((size_t)((step + 1) & 1) * groups + group) * ll_words;
-#pragma unroll
-        for (int it = 0; it < IPT; ++it) {
-            const int j = warp + it * kLstmWarps;
-            const int b = b0 + j;
-            const float gi = s_act[(0 * NB + j) * 32 + lane], gf = s_act[(1 * NB + j) * 32 + lane];
-            const float gg = s_act[(2 * NB + j) * 32 + lane], go = s_act[(3 * NB + j) * 32 + lane];
-            const float c = gf * c_state[it] + gi * gg;
-            c_state[it] = c;
-            const float h = go * tanh_f(c);
-            const bf16 hb = __float2bfloat16_rn(h);
-            const uint32_t mine = (uint32_t)__bfloat16_as_ushort(hb);
-            const uint32_t other = __shfl_down_sync(0xffffffffu, mine, 1);
-            if (!(lane & 1) && step + 1 < T)
-                st_volatile_u2(dst + (size_t)j * (H / 2) + (u * kUnits + lane) / 2, make_uint2(mine | (other << 16), (uint32_t)(step + 1)));
-            if (b < B) {
-                const size_t o = ((size_t)b * T + t) * (2 * H) + d * H + u * kUnits + lane;
-                p.Y[o] = hb;
-                if (p.C) p.C[o] = c;
-            }
+        // ---- 4 x 4 transpose inside each quad: lane `gate` ends up with {i, f, g, o} of batch row part*4 + gate ----
+        {
+            const bool b0_ = lane & 1, b1_ = lane & 2;
+            float x = b0_ ? a[0] : a[1], y = b0_ ? a[2] : a[3];
+            x = __shfl_xor_sync(0xffffffffu, x, 1);
+            y = __shfl_xor_sync(0xffffffffu, y, 1);
+            if (b0_) { a[0] = x; a[2] = y; } else { a[1] = x; a[3] = y; }
+            x = b1_ ? a[0] : a[2];
+            y = b1_ ? a[1] : a[3];
+            x = __shfl_xor_sync(0xffffffffu, x, 2);
+            y = __shfl_xor_sync(0xffffffffu, y, 2);
+            if (b1_) { a[0] = x; a[1] = y; } else { a[2] = x; a[3] = y; }
         }
-        PROF_MARK(3);                                   // cell update + stores
+        // ---- cell update + publish ----
+        const float c = a[1] * c_state + a[0] * a[2];
+        c_state = c;
+        const float h = a[3] * tanh_f(c);
+        const bf16 hb = __float2bfloat16_rn(h);
+        const uint32_t mine = (uint32_t)__bfloat16_as_ushort(hb);
+        const uint32_t other = __shfl_down_sync(0xffffffffu, mine, 4);       // same batch row, next unit
+        if (!(lane & 4) && step + 1 < T)
+            st_volatile_u2(p.ll + ((size_t)((step + 1) & 1) * groups + group) * ll_words + ll_mine,
+                           make_uint2(mine | (other << 16), (uint32_t)(step + 1)));
+        if (my_ok) {
+            *pY = hb;
+            if (pC) *pC = c;
+        }
+        pY += y_step;
+        if (pC) pC += y_step;
+        PROF_MARK(2);                                   // activation + cell update + stores
     }
     tc::fence_before_sync();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(tmem, tmem_cols);
 }
-
 
 // ======================================================================================
 // Backward recurrence.  Same groups / ownership as the forward pass.  Per step (reverse order):
@@ -347,8 +365,12 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_bwd_kernel(LstmBwdParams
     const size_t g_row = (size_t)2 * 4 * H;
     const unsigned short *G16 = reinterpret_cast<const unsigned short *>(p.G);
     const unsigned short *dY16 = reinterpret_cast<const unsigned short *>(p.dY);
-    auto g_index = [&](int t, int gate) { return ((size_t)b * T + t) * g_row + (size_t)d * 4 * H + (size_t)gate * H + u * kUnits + unit; };
-    auto y_index = [&](int t) { return ((size_t)b * T + t) * (2 * H) + d * H + u * kUnits + unit; };
+    // hoisted addressing: element offsets of (b, t, this unit) advance by a constant per step
+    const int t_first = d ? 0 : (T - 1);
+    const ptrdiff_t g_step = (ptrdiff_t)(d ? 1 : -1) * (ptrdiff_t)g_row;
+    const ptrdiff_t y_step = (ptrdiff_t)(d ? 1 : -1) * 2 * H;
+    size_t g_off = ((size_t)b * T + t_first) * g_row + (size_t)d * 4 * H + u * kUnits + unit;     // gate 0; gate g at + g*H
+    size_t y_off = ((size_t)b * T + t_first) * (2 * H) + d * H + u * kUnits + unit;
 
     float dc_carry = 0.f;
     // raw prefetch for the first step
@@ -357,11 +379,10 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_bwd_kernel(LstmBwdParams
     float rc, rcp;
     {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) rg[g] = G16[g_index(t, g)];
-        rdy = dY16[y_index(t)];
-        rc = p.C[y_index(t)];
-        const int tp = d ? (t + 1) : (t - 1);
-        rcp = (tp >= 0 && tp < T) ? p.C[y_index(tp)] : 0.f;
+        for (int g = 0; g < 4; ++g) rg[g] = G16[g_off + (size_t)g * H];
+        rdy = dY16[y_off];
+        rc = p.C[y_off];
+        rcp = (T > 1) ? p.C[y_off + y_step] : 0.f;          // c_{t-1} in forward order == next time index visited here
     }
     long long *prof = (g_prof && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? g_prof : nullptr;
     long long tprev = clock64();
@@ -376,24 +397,23 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_bwd_kernel(LstmBwdParams
             const int c_lo = half * c_half, c_hi = min(G, c_lo + c_half);
             float sx = 0.f, sy = 0.f;
             uint2 w[8];
+            const uint2 *wsrc = src + ((size_t)c_lo * (NB / 2) + jp) * 32 + lane;       // producer stride: (NB/2)*32 words
+            constexpr int PS = (NB / 2) * 32;
+            // spin on one word, then fetch the rest (see the forward kernel)
+            if (c_lo < c_hi) {
+                w[0] = ld_volatile_u2(wsrc);
+                while (w[0].y != (uint32_t)step) w[0] = ld_volatile_u2(wsrc);
+            }
 #pragma unroll
-            for (int n = 0; n < 8; ++n)
-                if (c_lo + n < c_hi) w[n] = ld_volatile_u2(src + ((size_t)(c_lo + n) * (NB / 2) + jp) * 32 + lane);
+            for (int n = 1; n < 8; ++n)
+                if (c_lo + n < c_hi) w[n] = ld_volatile_u2(wsrc + n * PS);
 #pragma unroll
             for (int n = 0; n < 8; ++n) {
                 if (c_lo + n < c_hi) {
-                    const uint2 *a = src + ((size_t)(c_lo + n) * (NB / 2) + jp) * 32 + lane;
-                    while (w[n].y != (uint32_t)step) w[n] = ld_volatile_u2(a);
+                    while (w[n].y != (uint32_t)step) w[n] = ld_volatile_u2(wsrc + n * PS);
                     sx += __uint_as_float(w[n].x << 16);
                     sy += __uint_as_float(w[n].x & 0xffff0000u);
                 }
-            }
-            for (int c = c_lo + 8; c < c_hi; ++c) {               // G > 16 (H > 512)
-                const uint2 *a = src + ((size_t)c * (NB / 2) + jp) * 32 + lane;
-                uint2 x = ld_volatile_u2(a);
-                while (x.y != (uint32_t)step) x = ld_volatile_u2(a);
-                sx += __uint_as_float(x.x << 16);
-                sy += __uint_as_float(x.x & 0xffff0000u);
             }
             s_part[(half * (NB / 2) + jp) * 32 + lane] = make_float2(sx, sy);
             __syncthreads();
@@ -417,16 +437,16 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_bwd_kernel(LstmBwdParams
         for (int g = 0; g < 4; ++g) {
             const bf16 v = __float2bfloat16_rn(da[g]);
             *reinterpret_cast<bf16 *>(sDA + tc::kmajor_off(j, g * 32 + unit, 128)) = v;
-            if (row_ok) p.G[g_index(t, g)] = v;
+            if (row_ok) p.G[g_off + (size_t)g * H] = v;
         }
+        g_off += g_step;
+        y_off += y_step;
         if (step + 1 < T) {                              // raw prefetch for the next step
-            const int tn = d ? (t + 1) : (t - 1);
 #pragma unroll
-            for (int g = 0; g < 4; ++g) rg[g] = G16[g_index(tn, g)];
-            rdy = dY16[y_index(tn)];
-            rc = p.C[y_index(tn)];
-            const int tp = d ? (tn + 1) : (tn - 1);
-            rcp = (tp >= 0 && tp < T) ? p.C[y_index(tp)] : 0.f;
+            for (int g = 0; g < 4; ++g) rg[g] = G16[g_off + (size_t)g * H];
+            rdy = dY16[y_off];
+            rc = p.C[y_off];
+            rcp = (step + 2 < T) ? p.C[y_off + y_step] : 0.f;
         }
         if (step + 1 == T) break;                        // dh_rec of the last step is never used
         tc::fence_proxy_async();
@@ -488,16 +508,15 @@ struct LstmPlan {
     size_t smem, ll_bytes;
 };
 int lstm_plan(int B, int H, LstmPlan &pl) {
-    MLVAE_REQUIRE(H % 32 == 0 && H >= 32 && H <= 768, MLVAE_ERR_UNSUPPORTED,
-                  "lstm: hidden size must be a multiple of 32 in [32, 768] (W_hh slice resident in tensor memory), got %d", H);
+    MLVAE_REQUIRE(H % 32 == 0 && H >= 32 && H <= 512, MLVAE_ERR_UNSUPPORTED,
+                  "lstm: hidden size must be a multiple of 32 in [32, 512] (W_hh slice resident in tensor memory), got %d", H);
     pl.G = H / kUnits;
     const int sms = sm_count();
-    pl.NB = g_lstm_min_nb;       // batch rows per CTA: smallest of {16, 32, 64} with every CTA co-resident (1 CTA / SM)
-    while (pl.NB < 64 && (int64_t)pl.G * ((B + pl.NB - 1) / pl.NB) * 2 > sms) pl.NB *= 2;
+    pl.NB = 16;                  // batch rows per CTA (MMA N); every CTA must be co-resident (1 CTA / SM)
     pl.slices = (B + pl.NB - 1) / pl.NB;
     MLVAE_REQUIRE((int64_t)pl.G * pl.slices * 2 <= sms, MLVAE_ERR_UNSUPPORTED,
                   "lstm: batch %d x hidden %d needs %d co-resident CTAs (> %d SMs)", B, H, pl.G * pl.slices * 2, sms);
-    pl.smem = (size_t)pl.NB * H * 2 + (size_t)4 * pl.NB * 32 * 4;
+    pl.smem = (size_t)pl.NB * H * 2;
     pl.ll_bytes = (size_t)2 * 2 * pl.slices * pl.NB * (H / 2) * sizeof(uint2);
     return MLVAE_OK;
 }
@@ -540,12 +559,8 @@ int mlvae_lstm_fwd(void *d_p, const void *d_whh, void *d_y, float *d_c, int B, i
     dim3 grid(pl.G, pl.slices, 2), block(kLstmThreads);
     const void *fn = nullptr;
     const int nch = (g_lstm_issuers == 1 || g_lstm_issuers == 2 || g_lstm_issuers == 4) ? g_lstm_issuers : 2;
-#define LSTM_PICK(NBV)                                                                    \
-    (nch == 1 ? (const void *)lstm_fwd_kernel<NBV, 1>                                     \
-              : nch == 2 ? (const void *)lstm_fwd_kernel<NBV, 2> : (const void *)lstm_fwd_kernel<NBV, 4>)
-    if (pl.NB == 16) fn = LSTM_PICK(16);
-    else if (pl.NB == 32) fn = LSTM_PICK(32);
-    else fn = (const void *)lstm_fwd_kernel<64, 2>;
+    fn = nch == 1 ? (const void *)lstm_fwd_kernel<16, 1>
+                  : nch == 2 ? (const void *)lstm_fwd_kernel<16, 2> : (const void *)lstm_fwd_kernel<16, 4>;
     MLVAE_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
     MLVAE_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, grid, block, args, pl.smem, st));
     return MLVAE_OK;
@@ -558,8 +573,6 @@ int mlvae_lstm_bwd(void *d_gates, const float *d_c, const void *d_dy, const void
     MLVAE_REQUIRE(B > 0 && T > 0 && H > 0 && T < (1 << 30), MLVAE_ERR_INVALID_ARG, "lstm_bwd: bad sizes");
     LstmPlan pl;
     if (int rc = lstm_plan(B, H, pl)) return rc;
-    MLVAE_REQUIRE(pl.NB == 16 || (int64_t)pl.G * ((B + 15) / 16) * 2 <= sm_count(), MLVAE_ERR_UNSUPPORTED,
-                  "lstm_bwd: batch %d x hidden %d does not fit one 16-row slice per CTA", B, H);
     const int slices = (B + 15) / 16;
     MLVAE_REQUIRE((int64_t)pl.G * slices * 2 <= sm_count(), MLVAE_ERR_UNSUPPORTED,
                   "lstm_bwd: batch %d x hidden %d needs %d co-resident CTAs", B, H, pl.G * slices * 2);

@@ -16,7 +16,7 @@ _scratch = {}
 
 
 def supported(x: torch.Tensor, hidden: int) -> bool:
-    return x.is_cuda and x.dtype == torch.bfloat16 and hidden % 32 == 0 and 32 <= hidden <= 768 \
+    return x.is_cuda and x.dtype == torch.bfloat16 and hidden % 32 == 0 and 32 <= hidden <= 512 \
         and L.lib().mlvae_lstm_scratch_bytes(x.shape[0], hidden) > 0
 
 
