@@ -234,6 +234,15 @@ def run_ours(args):
 
     for i in range(args.warmup):
         step_resident(i)
+    if args.profile and rank == 0:
+        from torch.profiler import ProfilerActivity, profile
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for i in range(3):
+                step_resident(i)
+            torch.cuda.synchronize()
+        with open(args.profile, "w") as f:
+            f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=90))
     # ---- kernel probe: the fused front-end inside the step, CUDA events on the launching stream
     fb_evs = []
     orig_features = ts.features
@@ -303,6 +312,7 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", default="", help="write a torch.profiler kernel table of 3 steps to this path")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -65,9 +65,15 @@ class _BiLSTMLayer(torch.autograd.Function):
         db = dA2.sum(0, dtype=torch.float32)
         dw_hh = torch.empty_like(w_hh)
         if T > 1:
-            # h_{t-1} in each direction's own order: forward uses y[:, t-1, :H], reverse uses y[:, t+1, H:]
-            dw_hh[0] = dA[:, 1:, 0].reshape(-1, 4 * H).t() @ y[:, :-1, :H].reshape(-1, H)
-            dw_hh[1] = dA[:, :-1, 1].reshape(-1, 4 * H).t() @ y[:, 1:, H:].reshape(-1, H)
+            # dW_hh[d] = sum_{b,t} dA[b,t,d]^T h_prev[b,t,d] with h_prev the previous step IN THAT DIRECTION'S ORDER
+            # (forward: y[b,t-1,:H]; reverse: y[b,t+1,H:]).  On the flattened (B*T) row axis that is one strided GEMM
+            # of rows r against rows r-1 (r+1) -- no copies -- minus the B-1 pairs that straddle two utterances.
+            y2 = y.view(B * T, 2 * H)
+            dw_hh[0] = dA2[1:, :4 * H].t() @ y2[:-1, :H]
+            dw_hh[1] = dA2[:-1, 4 * H:].t() @ y2[1:, H:]
+            if B > 1:
+                dw_hh[0] -= dA[1:, 0, 0].t() @ y[:-1, T - 1, :H]
+                dw_hh[1] -= dA[:-1, T - 1, 1].t() @ y[1:, 0, H:]
         else:
             dw_hh.zero_()
         return dx, dw_ih, dw_hh, db.to(torch.bfloat16), None
