@@ -13,6 +13,7 @@ import torch
 from . import _lib as L
 
 _scratch = {}
+PROBE = None      # bench.py sets this to a list; every recurrence launch then appends (tag, start_event, end_event)
 
 
 def supported(x: torch.Tensor, hidden: int) -> bool:
@@ -32,6 +33,21 @@ def _get_scratch(B, H, device):
     return buf
 
 
+def _probe_start():
+    if PROBE is None:
+        return None
+    e = torch.cuda.Event(enable_timing=True)
+    e.record()
+    return e
+
+
+def _probe_end(tag, start):
+    if start is not None:
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        PROBE.append((tag, start, e))
+
+
 class _BiLSTMLayer(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w_ih, w_hh, bias, training):
@@ -43,8 +59,10 @@ class _BiLSTMLayer(torch.autograd.Function):
         P = torch.addmm(bias, x2, w_ih.t()).view(B, T, 2, 4 * H)            # library GEMM (time-parallel)
         y = torch.empty(B, T, 2 * H, dtype=torch.bfloat16, device=x.device)
         c = torch.empty(B, T, 2 * H, dtype=torch.float32, device=x.device) if training else None
+        ev = _probe_start()
         L.check(L.lib().mlvae_lstm_fwd(L.ptr(P), L.ptr(w_hh), L.ptr(y), L.ptr(c), B, T, H, int(training),
                                        L.ptr(_get_scratch(B, H, x.device)), L.stream_ptr()), "mlvae_lstm_fwd")
+        _probe_end("lstm_fwd", ev)
         if training:
             ctx.save_for_backward(x, w_ih, w_hh, P, c, y)
         return y
@@ -55,8 +73,10 @@ class _BiLSTMLayer(torch.autograd.Function):
         B, T, In = x.shape
         H = w_hh.shape[2]
         dy = dy.contiguous().to(torch.bfloat16)
+        ev = _probe_start()
         L.check(L.lib().mlvae_lstm_bwd(L.ptr(gates), L.ptr(c), L.ptr(dy), L.ptr(w_hh), B, T, H,
                                        L.ptr(_get_scratch(B, H, x.device)), L.stream_ptr()), "mlvae_lstm_bwd")
+        _probe_end("lstm_bwd", ev)
         dA = gates                                                         # now pre-activation gradients (B,T,2,4H)
         dA2 = dA.view(B * T, 8 * H)
         x2 = x.reshape(B * T, In)
