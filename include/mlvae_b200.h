@@ -173,6 +173,12 @@ int mlvae_fbank_fwd(const mlvae_fbank_plan *plan, const float *d_wav, const int3
  * ------------------------------------------------------------------------- */
 /* Test hook: D (128 x N, f32) = A (128 x K, bf16) * B (N x K, bf16)^T through one
  * tcgen05.mma tile; checks the descriptor / TMEM conventions of csrc/tc05.cuh. */
+/* Y (M x N, bf16, row stride ldy) = act(X (M x K, bf16, row stride ldx) W (N x K, bf16)^T + bias (N, f32 or NULL)).
+ * One Linear (+ LeakyReLU(0.01) when leaky != 0) of modules/fc_block.py:9-16 on tcgen05 with the accumulator in
+ * TMEM.  N <= 256, K % 8 == 0, ldx % 8 == 0, X / W 16-byte aligned.  The input gradient of the same layer is the
+ * same call with W^T. */
+int mlvae_linear_fwd(const void *d_x, const void *d_w, const float *d_bias, void *d_y, int M, int N, int K,
+                     int ldx, int ldy, int leaky, void *stream);
 int mlvae_tc05_selftest(const void *d_a, const void *d_b, float *d_d, int N, int K, int a_in_tmem, void *stream);
 
 /* ------------------------------------------------------------------------- *

@@ -1,11 +1,13 @@
 """Dense (Linear / LeakyReLU) stacks of the latent block.
 
-Reference: modules/fc_block.py:4-21 (Linear -> LeakyReLU(0.01) ... last Linear bare,
-optional end activation; the ``dropout`` argument is accepted and ignored there).
+Reference: modules/fc_block.py:4-21 (Linear -> LeakyReLU(0.01) ... last Linear bare, optional end
+activation; the ``dropout`` argument is accepted and ignored there).
 
-Round-1 state: the projections are library GEMMs (cuBLAS through torch.nn.functional.linear)
--- they are HBM-bound skinny GEMMs (N <= 128) -- while the tcgen05/TMEM fused chain
-(csrc/gemm_chain.cu) is brought up; `linear_chain` is the single seam both go through.
+bf16 activations run every Linear(+LeakyReLU) on the tcgen05 / TMEM kernel ``mlvae_linear_fwd``
+(csrc/gemm_chain.cu): forward and the input gradient (the same kernel against W^T); the weight
+gradient dW = g^T x is a reduction over all B*T rows and stays a library GEMM in round 1, as does the
+whole stack in float32 (tensor cores would break the fp32 1e-5 parity).  ``linear_chain`` is the single
+seam every module goes through.
 """
 from __future__ import annotations
 
@@ -17,12 +19,62 @@ from . import _lib as L
 LEAKY_SLOPE = 0.01
 
 
+def _tc_ok(x2: torch.Tensor, n_out: int, k_in: int) -> bool:
+    return x2.dtype == torch.bfloat16 and n_out <= 256 and k_in % 8 == 0 and x2.stride(0) % 8 == 0
+
+
+def _launch(x2, w_bf16, bias_f32, n_out, leaky):
+    M, K = x2.shape
+    y = torch.empty(M, n_out, dtype=torch.bfloat16, device=x2.device)
+    L.check(L.lib().mlvae_linear_fwd(L.ptr(x2), L.ptr(w_bf16), L.ptr(bias_f32), L.ptr(y), M, n_out, K, x2.stride(0), n_out,
+                                     int(leaky), L.stream_ptr()), "mlvae_linear_fwd")
+    return y
+
+
+class _LinearTC(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x2, w, b, leaky):
+        wb = w.detach().to(torch.bfloat16).contiguous()
+        y = _launch(x2, wb, b.detach().float().contiguous(), w.shape[0], leaky)
+        ctx.save_for_backward(x2, wb, y if leaky else None)
+        ctx.leaky = leaky
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, wb, y = ctx.saved_tensors
+        g = dy.contiguous()
+        if ctx.leaky:
+            g = g * torch.where(y > 0, 1.0, LEAKY_SLOPE).to(g.dtype)
+        N, K = wb.shape
+        dx = None
+        if ctx.needs_input_grad[0]:
+            if _tc_ok(g, K, N):
+                dx = _launch(g, wb.t().contiguous(), None, K, False)      # dx = g W  ==  linear(g, W^T)
+            else:
+                dx = g @ wb
+        dw = (g.t() @ x2).float()
+        db = g.sum(0, dtype=torch.float32)
+        return dx, dw, db, None
+
+
+def linear(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, leaky: bool = False) -> torch.Tensor:
+    """x (..., K) -> act(x W^T + b) (..., N); w, b are the float32 master parameters."""
+    L.require_cuda(x)
+    lead = x.shape[:-1]
+    x2 = x.reshape(-1, x.shape[-1])
+    if _tc_ok(x2, w.shape[0], w.shape[1]):
+        y = _LinearTC.apply(x2.contiguous(), w, b, leaky)
+    else:
+        y = F.linear(x2, w.to(x.dtype), b.to(x.dtype))
+        if leaky:
+            y = F.leaky_relu(y, LEAKY_SLOPE)
+    return y.reshape(*lead, w.shape[0])
+
+
 def linear_chain(x: torch.Tensor, weights, biases, end_activation: bool = False) -> torch.Tensor:
     """x (..., K0) -> (..., N_last).  weights[i]: (N_i, K_i) float32 master copies."""
-    L.require_cuda(x)
     n = len(weights)
     for i, (w, b) in enumerate(zip(weights, biases)):
-        x = F.linear(x, w.to(x.dtype), b.to(x.dtype))
-        if i + 1 < n or end_activation:
-            x = F.leaky_relu(x, LEAKY_SLOPE)
+        x = linear(x, w, b, leaky=(i + 1 < n or end_activation))
     return x

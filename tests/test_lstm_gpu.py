@@ -85,3 +85,27 @@ def test_unsupported_hidden_size_is_refused(cuda):
     from ml_vae_b200 import _lib as L
     assert L.lib().mlvae_lstm_scratch_bytes(8, 48) == 0
     assert b"multiple of 32" in L.lib().mlvae_last_error()
+
+
+@pytest.mark.parametrize("M,K,N,leaky", [(128, 64, 64, False), (300, 80, 64, True), (4001, 1024, 128, True), (1000, 120, 64, True),
+                                          (513, 64, 120, False), (100, 8, 16, False), (2000, 64, 80, False), (999, 240, 64, True)])
+def test_tcgen05_linear_fwd_bwd_vs_torch(cuda, M, K, N, leaky):
+    """Linear(+LeakyReLU) on the tcgen05 kernel (forward and dX) against float32 torch on the same bf16 inputs."""
+    from ml_vae_b200 import dense
+    g = torch.Generator().manual_seed(M + K + N)
+    x = torch.randn(M, K, generator=g).bfloat16().to(cuda)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).bfloat16().float().to(cuda).requires_grad_(True)
+    b = torch.randn(N, generator=g).to(cuda).requires_grad_(True)
+    gy = torch.randn(M, N, generator=g).bfloat16().to(cuda)
+    xr = x.float().requires_grad_(True)
+    yr = torch.nn.functional.linear(xr, w, b)
+    if leaky:
+        yr = torch.nn.functional.leaky_relu(yr, 0.01)
+    gw, gb, gx = torch.autograd.grad((yr * gy.float()).sum(), [w, b, xr])
+    xm = x.clone().requires_grad_(True)
+    y = dense.linear(xm, w, b, leaky)
+    assert y.dtype == torch.bfloat16
+    hw, hb, hx = torch.autograd.grad((y.float() * gy.float()).sum(), [w, b, xm])
+    assert rel_err(y, yr) < BF16_RTOL
+    assert rel_err(hx, gx) < BF16_RTOL
+    assert rel_err(hw, gw) < BF16_RTOL and rel_err(hb, gb) < BF16_RTOL
