@@ -187,8 +187,9 @@ int mlvae_tc05_selftest(const void *d_a, const void *d_b, float *d_d, int N, int
  * timesteps is a plain GEMM done by the caller into d_p; this entry point walks the T
  * recurrent steps of BOTH directions in one cooperative launch (tcgen05 + TMEM, W_hh
  * resident in shared memory).  bf16 only; H % 32 == 0, H <= 512.
- *   d_p   (B, T, 2, 4H) bf16  gate pre-activations, torch gate order i,f,g,o; when
- *                             save_gates != 0 it is overwritten with the activated gates
+ *   d_p   (B, T, 2, H, 4) bf16 gate pre-activations, UNIT-major with the four gates i,f,g,o of a unit
+ *                             adjacent (permute the rows of W_ih / bias accordingly); when save_gates != 0
+ *                             it is overwritten with the activated gates
  *   d_whh (2, 4H, H)    bf16  weight_hh_l{k}, weight_hh_l{k}_reverse
  *   d_y   (B, T, 2H)    bf16  output (forward direction in [:H], reverse in [H:])
  *   d_c   (B, T, 2H)    f32   cell states for the backward pass, or NULL
@@ -202,7 +203,7 @@ int mlvae_debug_set_option(int key, int value);
 int mlvae_lstm_fwd(void *d_p, const void *d_whh, void *d_y, float *d_c, int B, int T, int H,
                    int save_gates, void *d_scratch, void *stream);
 
-/* Backward recurrence of the same layer.  d_gates: the (B,T,2,4H) buffer mlvae_lstm_fwd filled with
+/* Backward recurrence of the same layer.  d_gates: the (B,T,2,H,4) buffer mlvae_lstm_fwd filled with
  * activated gates (save_gates = 1); on return it holds the PRE-ACTIVATION gradients dA (bf16), from
  * which the caller forms dW_ih = dA^T x, dW_hh = dA^T h_prev, db = sum dA, dx = dA W_ih (plain GEMMs).
  * d_c: cell states from the forward pass; d_dy: (B,T,2H) bf16 gradient of the layer output. */

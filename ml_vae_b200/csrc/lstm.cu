@@ -50,7 +50,7 @@ __device__ long long *g_prof = nullptr;     // optional per-phase cycle counters
     } while (0)
 
 struct LstmFwdParams {
-    bf16 *P;                 // (B, T, 2, 4H) gate pre-activations from the input projection (+ biases);
+    bf16 *P;                 // (B, T, 2, H, 4) gate pre-activations (unit-major, the 4 gates i,f,g,o adjacent) from the input projection;
                              // overwritten with the ACTIVATED gates (i, f, g, o) when save != 0
     const bf16 *Whh;         // (2, 4H, H)
     bf16 *Y;                 // (B, T, 2H)
@@ -125,22 +125,17 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_fwd_kernel(LstmFwdParams
 
     // ---- per-thread constant addressing, hoisted out of the time loop ----
     const int t_first = d ? (T - 1) : 0;
-    const ptrdiff_t p_step = (ptrdiff_t)(d ? -1 : 1) * 2 * 4 * H;           // P elements per time step
+    const ptrdiff_t p_step = (ptrdiff_t)(d ? -1 : 1) * 2 * H;               // P stride per time step in 8-byte units
     const ptrdiff_t y_step = (ptrdiff_t)(d ? -1 : 1) * 2 * H;
-    unsigned short *pP[CPW];                                                 // (gate, unit) of batch rows part*4 + i
-    bool row_ok[CPW];
-#pragma unroll
-    for (int i = 0; i < CPW; ++i) {
-        const int b = b0 + part * CPW + i;
-        row_ok[i] = b < B;
-        pP[i] = reinterpret_cast<unsigned short *>(p.P) +
-                ((size_t)min(b, B - 1) * T + t_first) * (2 * 4 * H) + (size_t)d * 4 * H + (size_t)gate * H + u * kUnits + unit_local;
-    }
     const int my_row = part * CPW + gate;                                    // batch row this lane owns after the transpose
     const bool my_ok = (b0 + my_row) < B;
     const size_t y_off = ((size_t)min(b0 + my_row, B - 1) * T + t_first) * (2 * H) + d * H + u * kUnits + unit_local;
     bf16 *pY = p.Y + y_off;
     float *pC = p.C ? p.C + y_off : nullptr;
+    // gate buffer layout: (B, T, 2, H, 4) -- the four gates of a unit are adjacent, so the lane that owns (unit, batch
+    // row) after the transpose reads its pre-activations and writes its activated gates with ONE 8-byte access
+    uint2 *pG = reinterpret_cast<uint2 *>(p.P) +
+                (((size_t)min(b0 + my_row, B - 1) * T + t_first) * 2 + d) * (size_t)H + u * kUnits + unit_local;
     const size_t ll_mine = (size_t)my_row * (H / 2) + (u * kUnits + unit_local) / 2;
     constexpr int WB = 8;                                                    // exchange words per thread per round
     // word i = n * 512 + tid -> (batch row j, unit pair kw); its K-major byte offset is computed once (H <= 512
@@ -154,11 +149,9 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_fwd_kernel(LstmFwdParams
     }
     float c_state = 0.f;
 
-    // input-projection terms are prefetched one step ahead as RAW bf16 bits (converting at load time would
-    // stall the warp on the DRAM latency inside the step)
-    unsigned short pre_raw[CPW];
-#pragma unroll
-    for (int i = 0; i < CPW; ++i) pre_raw[i] = *pP[i];
+    // input-projection terms are prefetched one step ahead as RAW bits (converting at load time would stall the warp on
+    // the DRAM latency inside the step)
+    uint2 pre_raw = *pG;
 
     long long *prof = (g_prof && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? g_prof : nullptr;
     long long tprev = clock64();
@@ -223,22 +216,11 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_fwd_kernel(LstmFwdParams
 #pragma unroll
             for (int i = 0; i < CPW; ++i) acc[i] = 0.f;      // h_0 = 0
         }
-        // ---- gate non-linearity, divergence free: sigma(x) for i, f, o and tanh(x) = 2 sigma(2x) - 1 for g ----
-        const float kx = (gate == 2) ? 2.f : 1.f;
+        // ---- 4 x 4 transpose of the raw accumulators inside each quad: lane `gate` ends up with the {i, f, g, o}
+        //      pre-activations of batch row part*4 + gate for its unit ----
         float a[CPW];
 #pragma unroll
-        for (int i = 0; i < CPW; ++i) {
-            const float x = acc[i] + __uint_as_float((uint32_t)pre_raw[i] << 16);
-            const float sg = __fdividef(1.f, 1.f + __expf(-kx * x));
-            a[i] = (gate == 2) ? (2.f * sg - 1.f) : sg;
-            if (p.save && row_ok[i]) *pP[i] = __bfloat16_as_ushort(__float2bfloat16_rn(a[i]));
-            pP[i] += p_step;
-        }
-        if (step + 1 < T) {                              // prefetch next step's input projection
-#pragma unroll
-            for (int i = 0; i < CPW; ++i) pre_raw[i] = *pP[i];
-        }
-        // ---- 4 x 4 transpose inside each quad: lane `gate` ends up with {i, f, g, o} of batch row part*4 + gate ----
+        for (int i = 0; i < CPW; ++i) a[i] = acc[i];
         {
             const bool b0_ = lane & 1, b1_ = lane & 2;
             float x = b0_ ? a[0] : a[1], y = b0_ ? a[2] : a[3];
@@ -251,6 +233,12 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_fwd_kernel(LstmFwdParams
             y = __shfl_xor_sync(0xffffffffu, y, 2);
             if (b1_) { a[0] = x; a[1] = y; } else { a[2] = x; a[3] = y; }
         }
+        // ---- add the input projection (one 8-byte word: 4 gates) and apply the non-linearities ----
+        a[0] = sigmoid_f(a[0] + __uint_as_float(pre_raw.x << 16));
+        a[1] = sigmoid_f(a[1] + __uint_as_float(pre_raw.x & 0xffff0000u));
+        a[2] = tanh_f(a[2] + __uint_as_float(pre_raw.y << 16));
+        a[3] = sigmoid_f(a[3] + __uint_as_float(pre_raw.y & 0xffff0000u));
+        if (step + 1 < T) pre_raw = *(pG + p_step);      // prefetch next step's input projection (a full step to land)
         // ---- cell update + publish ----
         const float c = a[1] * c_state + a[0] * a[2];
         c_state = c;
@@ -261,12 +249,18 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_fwd_kernel(LstmFwdParams
         if (!(lane & 4) && step + 1 < T)
             st_volatile_u2(p.ll + ((size_t)((step + 1) & 1) * groups + group) * ll_words + ll_mine,
                            make_uint2(mine | (other << 16), (uint32_t)(step + 1)));
+        // ---- everything below is off the critical path: it overlaps the L2 flight time of the words just published ----
         if (my_ok) {
             *pY = hb;
             if (pC) *pC = c;
         }
         pY += y_step;
         if (pC) pC += y_step;
+        if (p.save && my_ok) {
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(a[0], a[1]), hi = __floats2bfloat162_rn(a[2], a[3]);
+            *pG = make_uint2(*reinterpret_cast<const uint32_t *>(&lo), *reinterpret_cast<const uint32_t *>(&hi));
+        }
+        pG += p_step;
         PROF_MARK(2);                                   // activation + cell update + stores
     }
     tc::fence_before_sync();
@@ -285,7 +279,7 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_fwd_kernel(LstmFwdParams
 //            CTA sums the G partial slices it receives in fixed producer order (deterministic)
 // ======================================================================================
 struct LstmBwdParams {
-    bf16 *G;                 // (B, T, 2, 4H) in: activated gates from the forward pass; out: pre-activation grads
+    bf16 *G;                 // (B, T, 2, H, 4) in: activated gates from the forward pass; out: pre-activation grads
     const float *C;          // (B, T, 2H) cell states from the forward pass
     const bf16 *dY;          // (B, T, 2H) gradient of the layer output
     const bf16 *Whh;         // (2, 4H, H)
@@ -363,23 +357,23 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_bwd_kernel(LstmBwdParams
     const int b = min(b0 + j, B - 1);                 // rows past B are clamped for loads, never stored
     const bool row_ok = (b0 + j) < B;
     const size_t g_row = (size_t)2 * 4 * H;
-    const unsigned short *G16 = reinterpret_cast<const unsigned short *>(p.G);
+    uint2 *G2 = reinterpret_cast<uint2 *>(p.G);
     const unsigned short *dY16 = reinterpret_cast<const unsigned short *>(p.dY);
     // hoisted addressing: element offsets of (b, t, this unit) advance by a constant per step
     const int t_first = d ? 0 : (T - 1);
-    const ptrdiff_t g_step = (ptrdiff_t)(d ? 1 : -1) * (ptrdiff_t)g_row;
+    const ptrdiff_t g_step = (ptrdiff_t)(d ? 1 : -1) * 2 * H;
     const ptrdiff_t y_step = (ptrdiff_t)(d ? 1 : -1) * 2 * H;
-    size_t g_off = ((size_t)b * T + t_first) * g_row + (size_t)d * 4 * H + u * kUnits + unit;     // gate 0; gate g at + g*H
+    size_t g_off = (((size_t)b * T + t_first) * 2 + d) * (size_t)H + u * kUnits + unit;        // 8-byte units: (B,T,2,H,4)
     size_t y_off = ((size_t)b * T + t_first) * (2 * H) + d * H + u * kUnits + unit;
 
     float dc_carry = 0.f;
     // raw prefetch for the first step
     int t = d ? 0 : (T - 1);
-    unsigned short rg[4], rdy;
+    uint2 rg;
+    unsigned short rdy;
     float rc, rcp;
     {
-#pragma unroll
-        for (int g = 0; g < 4; ++g) rg[g] = G16[g_off + (size_t)g * H];
+        rg = G2[g_off];
         rdy = dY16[y_off];
         rc = p.C[y_off];
         rcp = (T > 1) ? p.C[y_off + y_step] : 0.f;          // c_{t-1} in forward order == next time index visited here
@@ -422,8 +416,8 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_bwd_kernel(LstmBwdParams
         }
         PROF_MARK(0);                                   // partial gather + reduce
         // ---- phase A: gate gradients ----
-        const float gi = __uint_as_float((uint32_t)rg[0] << 16), gf = __uint_as_float((uint32_t)rg[1] << 16);
-        const float gg = __uint_as_float((uint32_t)rg[2] << 16), go = __uint_as_float((uint32_t)rg[3] << 16);
+        const float gi = __uint_as_float(rg.x << 16), gf = __uint_as_float(rg.x & 0xffff0000u);
+        const float gg = __uint_as_float(rg.y << 16), go = __uint_as_float(rg.y & 0xffff0000u);
         const float dh = __uint_as_float((uint32_t)rdy << 16) + dh_rec;
         const float tc_ = tanh_f(rc);
         const float dc = dc_carry + dh * go * (1.f - tc_ * tc_);
@@ -433,22 +427,28 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_bwd_kernel(LstmBwdParams
         const float da_o = dh * tc_ * go * (1.f - go);
         dc_carry = dc * gf;
         const float da[4] = {da_i, da_f, da_g, da_o};
+        bf16 dab[4];
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-            const bf16 v = __float2bfloat16_rn(da[g]);
-            *reinterpret_cast<bf16 *>(sDA + tc::kmajor_off(j, g * 32 + unit, 128)) = v;
-            if (row_ok) p.G[g_off + (size_t)g * H] = v;
+            dab[g] = __float2bfloat16_rn(da[g]);
+            *reinterpret_cast<bf16 *>(sDA + tc::kmajor_off(j, g * 32 + unit, 128)) = dab[g];
         }
-        g_off += g_step;
-        y_off += y_step;
-        if (step + 1 < T) {                              // raw prefetch for the next step
-#pragma unroll
-            for (int g = 0; g < 4; ++g) rg[g] = G16[g_off + (size_t)g * H];
-            rdy = dY16[y_off];
-            rc = p.C[y_off];
-            rcp = (step + 2 < T) ? p.C[y_off + y_step] : 0.f;
-        }
-        if (step + 1 == T) break;                        // dh_rec of the last step is never used
+        auto store_and_prefetch = [&]() {                // global side effects of phase A, issued after the MMAs are in flight
+            if (row_ok) {
+                const uint32_t lo = (uint32_t)__bfloat16_as_ushort(dab[0]) | ((uint32_t)__bfloat16_as_ushort(dab[1]) << 16);
+                const uint32_t hi = (uint32_t)__bfloat16_as_ushort(dab[2]) | ((uint32_t)__bfloat16_as_ushort(dab[3]) << 16);
+                G2[g_off] = make_uint2(lo, hi);
+            }
+            g_off += g_step;
+            y_off += y_step;
+            if (step + 1 < T) {                          // raw prefetch for the next step
+                rg = G2[g_off];
+                rdy = dY16[y_off];
+                rc = p.C[y_off];
+                rcp = (step + 2 < T) ? p.C[y_off + y_step] : 0.f;
+            }
+        };
+        if (step + 1 == T) { store_and_prefetch(); break; }     // dh_rec of the last step is never used
         tc::fence_proxy_async();
         tc::fence_before_sync();
         __syncthreads();
@@ -467,6 +467,7 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_bwd_kernel(LstmBwdParams
             }
             __syncwarp();
         }
+        store_and_prefetch();
         tc::mbar_wait(&s_bar, step & 1);
         tc::fence_after_sync();
         PROF_MARK(2);                                   // MMA

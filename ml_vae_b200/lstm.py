@@ -33,6 +33,22 @@ def _get_scratch(B, H, device):
     return buf
 
 
+_perm_cache = {}
+
+
+def _gate_perm(H: int, device):
+    """Row permutation torch order (dir, gate, unit) -> kernel order (dir, unit, gate) of the stacked (8H, .) matrices,
+    and its inverse.  The recurrence kernels keep the four gates of a unit adjacent (one 8-byte access per lane)."""
+    key = (H, device)
+    if key not in _perm_cache:
+        one = torch.arange(4 * H, device=device).view(4, H).t().reshape(-1)          # new (unit*4+gate) -> old (gate*H+unit)
+        perm = torch.cat([one, one + 4 * H])
+        inv = torch.empty_like(perm)
+        inv[perm] = torch.arange(8 * H, device=device)
+        _perm_cache[key] = (perm, inv)
+    return _perm_cache[key]
+
+
 def _probe_start():
     if PROBE is None:
         return None
@@ -56,7 +72,9 @@ class _BiLSTMLayer(torch.autograd.Function):
         B, T, In = x.shape
         H = w_hh.shape[2]
         x2 = x.reshape(B * T, In)
-        P = torch.addmm(bias, x2, w_ih.t()).view(B, T, 2, 4 * H)            # library GEMM (time-parallel)
+        perm, _ = _gate_perm(H, x.device)
+        w_ih_p = w_ih[perm]                                                   # rows in (dir, unit, gate) order
+        P = torch.addmm(bias[perm], x2, w_ih_p.t()).view(B, T, 2, 4 * H)     # library GEMM (time-parallel)
         y = torch.empty(B, T, 2 * H, dtype=torch.bfloat16, device=x.device)
         c = torch.empty(B, T, 2 * H, dtype=torch.float32, device=x.device) if training else None
         ev = _probe_start()
@@ -64,12 +82,12 @@ class _BiLSTMLayer(torch.autograd.Function):
                                        L.ptr(_get_scratch(B, H, x.device)), L.stream_ptr()), "mlvae_lstm_fwd")
         _probe_end("lstm_fwd", ev)
         if training:
-            ctx.save_for_backward(x, w_ih, w_hh, P, c, y)
+            ctx.save_for_backward(x, w_ih_p, w_hh, P, c, y)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, w_ih, w_hh, gates, c, y = ctx.saved_tensors
+        x, w_ih_p, w_hh, gates, c, y = ctx.saved_tensors
         B, T, In = x.shape
         H = w_hh.shape[2]
         dy = dy.contiguous().to(torch.bfloat16)
@@ -77,23 +95,26 @@ class _BiLSTMLayer(torch.autograd.Function):
         L.check(L.lib().mlvae_lstm_bwd(L.ptr(gates), L.ptr(c), L.ptr(dy), L.ptr(w_hh), B, T, H,
                                        L.ptr(_get_scratch(B, H, x.device)), L.stream_ptr()), "mlvae_lstm_bwd")
         _probe_end("lstm_bwd", ev)
-        dA = gates                                                         # now pre-activation gradients (B,T,2,4H)
-        dA2 = dA.view(B * T, 8 * H)
+        dA = gates                                                         # now pre-activation gradients (B,T,2,H,4)
+        dA2 = dA.view(B * T, 8 * H)                                        # columns in (dir, unit, gate) order
+        _, inv = _gate_perm(H, x.device)
         x2 = x.reshape(B * T, In)
-        dx = (dA2 @ w_ih).view(B, T, In)
-        dw_ih = dA2.t() @ x2
-        db = dA2.sum(0, dtype=torch.float32)
+        dx = (dA2 @ w_ih_p).view(B, T, In)
+        dw_ih = (dA2.t() @ x2)[inv]
+        db = dA2.sum(0, dtype=torch.float32)[inv]
         dw_hh = torch.empty_like(w_hh)
         if T > 1:
             # dW_hh[d] = sum_{b,t} dA[b,t,d]^T h_prev[b,t,d] with h_prev the previous step IN THAT DIRECTION'S ORDER
             # (forward: y[b,t-1,:H]; reverse: y[b,t+1,H:]).  On the flattened (B*T) row axis that is one strided GEMM
             # of rows r against rows r-1 (r+1) -- no copies -- minus the B-1 pairs that straddle two utterances.
             y2 = y.view(B * T, 2 * H)
-            dw_hh[0] = dA2[1:, :4 * H].t() @ y2[:-1, :H]
-            dw_hh[1] = dA2[:-1, 4 * H:].t() @ y2[1:, H:]
+            g0 = dA2[1:, :4 * H].t() @ y2[:-1, :H]
+            g1 = dA2[:-1, 4 * H:].t() @ y2[1:, H:]
             if B > 1:
-                dw_hh[0] -= dA[1:, 0, 0].t() @ y[:-1, T - 1, :H]
-                dw_hh[1] -= dA[:-1, T - 1, 1].t() @ y[1:, 0, H:]
+                g0 -= dA[1:, 0, 0].t() @ y[:-1, T - 1, :H]
+                g1 -= dA[:-1, T - 1, 1].t() @ y[1:, 0, H:]
+            dw_hh[0] = g0[inv[:4 * H]]
+            dw_hh[1] = g1[inv[:4 * H]]
         else:
             dw_hh.zero_()
         return dx, dw_ih, dw_hh, db.to(torch.bfloat16), None

@@ -22,7 +22,9 @@ def run(B, T, In, H, time_it=False, issuers=2, nb=16):
         ref, (hn, cn) = lstm(x)
     wih = torch.cat([lstm.weight_ih_l0, lstm.weight_ih_l0_reverse], 0)                   # (8H, In)
     bias = torch.cat([lstm.bias_ih_l0 + lstm.bias_hh_l0, lstm.bias_ih_l0_reverse + lstm.bias_hh_l0_reverse], 0)
-    P = (x @ wih.t() + bias).bfloat16().contiguous()                                         # (B, T, 8H) = (B,T,2,4H)
+    from ml_vae_b200.lstm import _gate_perm
+    perm, _ = _gate_perm(H, dev)
+    P = (x @ wih[perm].t() + bias[perm]).bfloat16().contiguous()                             # (B, T, 8H) = (B,T,2,H,4)
     whh = torch.stack([lstm.weight_hh_l0, lstm.weight_hh_l0_reverse], 0).bfloat16().contiguous()
     Y = torch.full((B, T, 2 * H), float("nan"), device=dev, dtype=torch.bfloat16)
     C = torch.empty(B, T, 2 * H, device=dev)
