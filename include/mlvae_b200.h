@@ -206,9 +206,11 @@ int mlvae_lstm_fwd(void *d_p, const void *d_whh, void *d_y, float *d_c, int B, i
 /* Backward recurrence of the same layer.  d_gates: the (B,T,2,H,4) buffer mlvae_lstm_fwd filled with
  * activated gates (save_gates = 1); on return it holds the PRE-ACTIVATION gradients dA (bf16), from
  * which the caller forms dW_ih = dA^T x, dW_hh = dA^T h_prev, db = sum dA, dx = dA W_ih (plain GEMMs).
- * d_c: cell states from the forward pass; d_dy: (B,T,2H) bf16 gradient of the layer output. */
-int mlvae_lstm_bwd(void *d_gates, const float *d_c, const void *d_dy, const void *d_whh, int B, int T, int H,
-                   void *d_scratch, void *stream);
+ * d_c: cell states from the forward pass; d_dy: (B,T,2H) bf16 gradient of the layer output.
+ * d_bias_grad_part (may be NULL): (ceil(B/16), 2, 4H) float32, per-16-row-slice sums of dA over rows and time in
+ * torch gate order; summing it over the first axis gives the bias gradient (deterministic). */
+int mlvae_lstm_bwd(void *d_gates, const float *d_c, const void *d_dy, const void *d_whh, float *d_bias_grad_part,
+                   int B, int T, int H, void *d_scratch, void *stream);
 
 #ifdef __cplusplus
 }

@@ -43,7 +43,7 @@ SIGNATURES = {
     "mlvae_debug_set_option": (_i, [_i, _i]),
     "mlvae_lstm_scratch_bytes": (_sz, [_i, _i]),
     "mlvae_lstm_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
-    "mlvae_lstm_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "mlvae_lstm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "mlvae_linear_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "mlvae_tc05_selftest": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "mlvae_fbank_fwd": (_i, [_vp, _vp, _vp, _i, _i64, _i64, _i, _vp, _i, _i, _vp, _vp, _vp]),

@@ -284,6 +284,7 @@ struct LstmBwdParams {
     const bf16 *dY;          // (B, T, 2H) gradient of the layer output
     const bf16 *Whh;         // (2, 4H, H)
     uint2 *ll;               // [2 parity][groups][G consumers][G producers][NB/2][32] zeroed {data, tag} words
+    float *db_part;          // (slices, 2, 4H) per-batch-slice sums over (rows, t) of dA, torch gate order; or nullptr
     int B, T, H;
 };
 
@@ -367,6 +368,7 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_bwd_kernel(LstmBwdParams
     size_t y_off = ((size_t)b * T + t_first) * (2 * H) + d * H + u * kUnits + unit;
 
     float dc_carry = 0.f;
+    float bsum[4] = {0.f, 0.f, 0.f, 0.f};             // bias gradient: sum over t of this (row, unit)'s dA, per gate
     // raw prefetch for the first step
     int t = d ? 0 : (T - 1);
     uint2 rg;
@@ -431,6 +433,7 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_bwd_kernel(LstmBwdParams
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
             dab[g] = __float2bfloat16_rn(da[g]);
+            if (row_ok) bsum[g] += __bfloat162float(dab[g]);
             *reinterpret_cast<bf16 *>(sDA + tc::kmajor_off(j, g * 32 + unit, 128)) = dab[g];
         }
         auto store_and_prefetch = [&]() {                // global side effects of phase A, issued after the MMAs are in flight
@@ -493,6 +496,20 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_bwd_kernel(LstmBwdParams
     }
     tc::fence_before_sync();
     __syncthreads();
+    if (p.db_part) {
+        // bias gradient of this CTA's 128 gate rows over its batch slice: fixed-order sum over the 16 rows (warps)
+        float *s_b = reinterpret_cast<float *>(smem);                    // [16 rows][4 gates][32 units], reuses sDA + s_part
+#pragma unroll
+        for (int g = 0; g < 4; ++g) s_b[(warp * 4 + g) * 32 + lane] = bsum[g];
+        __syncthreads();
+        if (tid < 128) {
+            const int g = tid >> 5, un = tid & 31;
+            float acc = 0.f;
+#pragma unroll
+            for (int r = 0; r < NB; ++r) acc += s_b[(r * 4 + g) * 32 + un];
+            p.db_part[((size_t)slice * 2 + d) * 4 * H + (size_t)g * H + u * kUnits + un] = acc;
+        }
+    }
     if (warp == 0) tc::tmem_dealloc(tmem, tmem_cols);
 }
 
@@ -568,8 +585,8 @@ int mlvae_lstm_fwd(void *d_p, const void *d_whh, void *d_y, float *d_c, int B, i
 }
 
 
-int mlvae_lstm_bwd(void *d_gates, const float *d_c, const void *d_dy, const void *d_whh, int B, int T, int H,
-                   void *d_scratch, void *stream) {
+int mlvae_lstm_bwd(void *d_gates, const float *d_c, const void *d_dy, const void *d_whh, float *d_bias_grad_part, int B, int T,
+                   int H, void *d_scratch, void *stream) {
     MLVAE_REQUIRE(d_gates && d_c && d_dy && d_whh && d_scratch, MLVAE_ERR_INVALID_ARG, "lstm_bwd: missing buffers");
     MLVAE_REQUIRE(B > 0 && T > 0 && H > 0 && T < (1 << 30), MLVAE_ERR_INVALID_ARG, "lstm_bwd: bad sizes");
     LstmPlan pl;
@@ -580,12 +597,12 @@ int mlvae_lstm_bwd(void *d_gates, const float *d_c, const void *d_dy, const void
     const size_t ll_bytes = (size_t)2 * 2 * slices * pl.G * pl.G * 8 * 32 * sizeof(uint2);
     cudaStream_t st = (cudaStream_t)stream;
     MLVAE_CHECK_CUDA(cudaMemsetAsync(d_scratch, 0, ll_bytes, st));
-    LstmBwdParams prm{(bf16 *)d_gates, d_c, (const bf16 *)d_dy, (const bf16 *)d_whh, (uint2 *)d_scratch, B, T, H};
+    LstmBwdParams prm{(bf16 *)d_gates, d_c, (const bf16 *)d_dy, (const bf16 *)d_whh, (uint2 *)d_scratch, d_bias_grad_part, B, T, H};
     void *args[] = {&prm};
     dim3 grid(pl.G, slices, 2), block(kLstmThreads);
     const void *fn = (g_lstm_issuers == 1) ? (const void *)lstm_bwd_kernel<16, 1>
                      : (g_lstm_issuers == 4) ? (const void *)lstm_bwd_kernel<16, 4> : (const void *)lstm_bwd_kernel<16, 2>;
-    const size_t smem = 16 * 128 * 2 + 2 * 8 * 32 * sizeof(float2);
+    const size_t smem = 16 * 4 * 32 * sizeof(float);       // >= sDA (4 KB) + s_part (4 KB); reused for the bias-gradient reduction
     MLVAE_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, grid, block, args, smem, st));
     return MLVAE_OK;
 }

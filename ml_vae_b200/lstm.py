@@ -92,7 +92,8 @@ class _BiLSTMLayer(torch.autograd.Function):
         H = w_hh.shape[2]
         dy = dy.contiguous().to(torch.bfloat16)
         ev = _probe_start()
-        L.check(L.lib().mlvae_lstm_bwd(L.ptr(gates), L.ptr(c), L.ptr(dy), L.ptr(w_hh), B, T, H,
+        db_part = torch.empty((B + 15) // 16, 8 * H, dtype=torch.float32, device=x.device)
+        L.check(L.lib().mlvae_lstm_bwd(L.ptr(gates), L.ptr(c), L.ptr(dy), L.ptr(w_hh), L.ptr(db_part), B, T, H,
                                        L.ptr(_get_scratch(B, H, x.device)), L.stream_ptr()), "mlvae_lstm_bwd")
         _probe_end("lstm_bwd", ev)
         dA = gates                                                         # now pre-activation gradients (B,T,2,H,4)
@@ -101,7 +102,7 @@ class _BiLSTMLayer(torch.autograd.Function):
         x2 = x.reshape(B * T, In)
         dx = (dA2 @ w_ih_p).view(B, T, In)
         dw_ih = (dA2.t() @ x2)[inv]
-        db = dA2.sum(0, dtype=torch.float32)[inv]
+        db = db_part.sum(0)                                                # bias gradient, reduced inside the kernel
         dw_hh = torch.empty_like(w_hh)
         if T > 1:
             # dW_hh[d] = sum_{b,t} dA[b,t,d]^T h_prev[b,t,d] with h_prev the previous step IN THAT DIRECTION'S ORDER
