@@ -40,34 +40,46 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region.  nvidia-smi needs ~0.2 s to start, so
+    the sampler is started before the warm-up and only the rows stamped inside [mark_start, mark_end] are kept."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
         self.rows, self.proc, self.index = [], None, index
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.index), "-lms", "20"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
+        inside = [r for t, r in self.rows if self.t0 is not None and self.t0 <= t <= (self.t1 or t) + 0.02]
+        where = "timed region"
+        if not inside:                                   # region shorter than one sampling period
+            inside, where = [r for _, r in self.rows[-3:]], "nearest samples (timed region shorter than the sampling period)"
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in inside:
             try:
                 sm.append(float(r[0])); mx = float(r[1])
             except Exception:
@@ -77,7 +89,7 @@ class ClockSampler:
                     reasons.add(n)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": where}
 
 
 # --------------------------------------------------------------------------------------------
@@ -232,6 +244,9 @@ def run_ours(args):
         loss = ts.step(stage, lens_abs)
         return float(loss.cpu())                                # D2H read of the step's result
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for i in range(args.warmup):
         step_resident(i)
     if args.profile and rank == 0:
@@ -258,11 +273,10 @@ def run_ours(args):
     ts.features = probed_features
     from ml_vae_b200 import lstm as lstm_mod
     lstm_mod.PROBE = []
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     L.LAUNCHES = 0
+    sampler.mark_start()
     sec, wall = timed(step_resident, args.steps)
+    sampler.mark_end()
     launches = getattr(L, "LAUNCHES", 0)
     clocks = sampler.stop() if rank == 0 else None
     ts.features = orig_features

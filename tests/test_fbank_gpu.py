@@ -70,6 +70,17 @@ def test_batched_ragged_vs_per_utterance_oracle(cuda, hop_ms, n_mels, deltas):
     assert_close(got16[:, :t].float(), want, BF16_RTOL, "bf16 features")
 
 
+def test_generic_hop_path(cuda):
+    """hop = 12.5 ms (200 samples, not a multiple of 16) takes the generic kernel; 10 / 20 ms take the specialised one."""
+    g = torch.Generator().manual_seed(4)
+    wav = 0.1 * torch.randn(3, 8000, generator=g)
+    for hop_ms in (12.5, 10, 20):
+        want = fbank_ref.fbank(wav, True, 16000, hop_ms, 400, 40, torch.float64)
+        got = _fb(deltas=True, hop_length=hop_ms, n_mels=40)(wav.to(cuda))
+        assert got.shape == want.shape
+        assert_close(got, want, FP32_RTOL, f"hop {hop_ms} ms")
+
+
 def test_silence_and_clamp(cuda):
     """Digital silence -> clamp(1e-10) -> -100 dB everywhere; mixed -> floor at max-80 dB."""
     fb = _fb(deltas=False, hop_length=10, n_mels=80)
