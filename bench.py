@@ -247,6 +247,9 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    graphed = False
+    if not args.no_graph:
+        graphed = ts.capture(resident[0], lens_abs, warmup=max(1, args.warmup))
     for i in range(args.warmup):
         step_resident(i)
     if args.profile and rank == 0:
@@ -277,8 +280,19 @@ def run_ours(args):
     sampler.mark_start()
     sec, wall = timed(step_resident, args.steps)
     sampler.mark_end()
-    launches = getattr(L, "LAUNCHES", 0)
     clocks = sampler.stop() if rank == 0 else None
+    # per-kernel durations: CUDA events around the launches.  A graph replay exposes no per-kernel events, so when the
+    # step is captured the probe runs on 3 extra EAGER steps of the same step function right after the timed region.
+    probe_steps = args.steps
+    if graphed:
+        L.LAUNCHES = 0
+        fb_evs.clear()
+        lstm_mod.PROBE = []
+        probe_steps = 3
+        for i in range(probe_steps):
+            ts._step_eager(resident[i % R], lens_abs)
+        torch.cuda.synchronize()
+    launches = getattr(L, "LAUNCHES", 0) * (args.steps / probe_steps)
     ts.features = orig_features
     fb_ms = sum(a.elapsed_time(b) for a, b in fb_evs) / max(len(fb_evs), 1)
     lstm_ms = {}
@@ -307,14 +321,14 @@ def run_ours(args):
         flops = 2.0 * B * T_frames * (4 * H) * H * 2                     # h W_hh^T (fwd) or dA W_hh (bwd), two directions
         allms = [v for vs in lstm_ms.values() for v in vs]
         per_launch = sum(allms) / len(allms)
-        per_step = sum(allms) / args.steps
+        per_step = sum(allms) / probe_steps
         for tag, vs in lstm_ms.items():
             m = sum(vs) / len(vs)
-            kernels[tag + "_kernel"] = {"ms_per_launch": round(m, 4), "launches_per_step": len(vs) // args.steps, "bound": "tensor",
+            kernels[tag + "_kernel"] = {"ms_per_launch": round(m, 4), "launches_per_step": len(vs) // probe_steps, "bound": "tensor",
                                         "algorithmic_flops": flops, "achieved_tflops": round(flops / (m * 1e-3) / 1e12, 1),
                                         "frac_of_bf16_sustained_peak": round(flops / (m * 1e-3) / 1e12 / tflops_peak, 4),
                                         "us_per_timestep": round(m * 1e3 / T_frames, 3),
-                                        "share_of_step": round(sum(vs) / args.steps / step_ms, 4)}
+                                        "share_of_step": round(sum(vs) / probe_steps / step_ms, 4)}
         roof = {"bound": "tensor", "kernel": "persistent biLSTM recurrence (lstm_fwd_kernel + lstm_bwd_kernel, tcgen05 + TMEM-resident W_hh)",
                 "achieved": round(flops / (per_launch * 1e-3) / 1e12, 1), "peak": tflops_peak, "unit": "TFLOP/s",
                 "frac": round(flops / (per_launch * 1e-3) / 1e12 / tflops_peak, 4), "traffic": 386e6 * T_frames / 300,
@@ -335,9 +349,9 @@ def run_ours(args):
             "config": workload_config(world, B),
             "e2e": {"value": round(e2e, 2), "unit": UNIT, "h2d_bytes_per_step": B * n * 4 * world,
                     "d2h_bytes_per_step": 4 * world, "ms_per_step": round(sec_e2e / args.steps * 1e3, 4)},
-            "gpu_launches": launches, "roofline": roof, "kernels": kernels,
+            "gpu_launches": int(round(launches)), "roofline": roof, "kernels": kernels,
             "library_calls": "time-parallel GEMMs (LSTM input projection / dX / dW, dense heads) are cuBLAS through torch in round 1",
-            "clocks": clocks, "wall_s": round(wall, 3)}
+            "clocks": clocks, "wall_s": round(wall, 3), "cuda_graph": graphed}
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             v, dt, cores = time_cpu_reference(8, 2, 1)
@@ -359,6 +373,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", default="", help="write a torch.profiler kernel table of 3 steps to this path")
+    ap.add_argument("--no-graph", action="store_true", help="do not capture the step in a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

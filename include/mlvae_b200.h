@@ -86,12 +86,14 @@ int mlvae_philox_normal(uint64_t seed, uint64_t offset, int64_t n, void *d_out, 
  *   d_kl_out = { sum(kl*mask) / (count*L), sum(kl*mask), count*L }     float[3]
  *
  * d_mu, d_logvar, d_z, d_kl_elem: (B,T,L) contiguous, element type `dtype`.
- * d_eps: same shape/dtype, or NULL to draw from Philox(seed, offset).
+ * d_eps: same shape/dtype, or NULL to draw from Philox(seed, offset + *d_offset_add).
+ * d_offset_add: optional DEVICE uint64 added to `offset` (a device-resident step counter keeps a
+ *   captured CUDA graph drawing fresh eps on every replay); NULL = 0.
  * d_kl_elem (unreduced KL, the reference module contract) may be NULL.
  * d_kl_out may be NULL (then d_lens and d_scratch may be NULL too).
  * ------------------------------------------------------------------------- */
 int mlvae_reparam_kl_fwd(const void *d_mu, const void *d_logvar, const void *d_eps,
-                         uint64_t seed, uint64_t offset, const float *d_lens,
+                         uint64_t seed, uint64_t offset, const uint64_t *d_offset_add, const float *d_lens,
                          int B, int T, int L, int dtype,
                          void *d_z, void *d_kl_elem, float *d_kl_out, void *d_scratch,
                          void *stream);
@@ -101,7 +103,7 @@ int mlvae_reparam_kl_fwd(const void *d_mu, const void *d_logvar, const void *d_e
  *   grad_logvar = grad_z * 0.5*exp(0.5*logvar)*eps + g_elem * 0.5*(exp(logvar) - 1)
  * d_grad_z may be NULL (treated as zero).  d_grad_kl_mean is a DEVICE float scalar. */
 int mlvae_reparam_kl_bwd(const void *d_mu, const void *d_logvar, const void *d_eps,
-                         uint64_t seed, uint64_t offset, const void *d_grad_z,
+                         uint64_t seed, uint64_t offset, const uint64_t *d_offset_add, const void *d_grad_z,
                          const void *d_grad_kl_elem, const float *d_grad_kl_mean,
                          const float *d_lens, int B, int T, int L, int dtype,
                          void *d_grad_mu, void *d_grad_logvar, void *stream);
@@ -166,6 +168,17 @@ int mlvae_fbank_fwd(const mlvae_fbank_plan *plan, const float *d_wav, const int3
                     int B, int64_t n_max, int64_t n_stride, int truncate_kaldi,
                     void *d_out, int out_dtype, int t_out, int32_t *d_out_frames,
                     void *d_scratch, void *stream);
+
+/* ------------------------------------------------------------------------- *
+ * Global input normalisation = speechbrain.processing.features.InputNormalization(norm_type='global')
+ * (models/test_vanilla_vae/model.yaml:14-15, model.py:24-25; arithmetic SB-recall): per-utterance mean /
+ * unbiased std over round(len*T) valid frames, batch average, running update with weight 1/(count+1).
+ * State {count, pad[3], glob_mean[D], glob_std[D]} lives on the device (zero it once).
+ * ------------------------------------------------------------------------- */
+size_t mlvae_norm_state_bytes(int D);
+size_t mlvae_norm_scratch_bytes(int B, int D);
+int mlvae_global_norm(const float *d_x, const float *d_lens, int B, int T, int D, int training, int update_stats,
+                      float *d_state, float *d_scratch, void *d_out, int out_dtype, void *stream);
 
 /* ------------------------------------------------------------------------- *
  * tcgen05 / TMEM dense projections (modules/fc_block.py:4-21 and the mean/log_var

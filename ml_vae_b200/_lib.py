@@ -28,8 +28,8 @@ SIGNATURES = {
     "mlvae_reduce_scratch_bytes": (_sz, []),
     "mlvae_philox_u32": (_i, [_u64, _u64, _i64, _vp, _vp]),
     "mlvae_philox_normal": (_i, [_u64, _u64, _i64, _vp, _i, _vp]),
-    "mlvae_reparam_kl_fwd": (_i, [_vp, _vp, _vp, _u64, _u64, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
-    "mlvae_reparam_kl_bwd": (_i, [_vp, _vp, _vp, _u64, _u64, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "mlvae_reparam_kl_fwd": (_i, [_vp, _vp, _vp, _u64, _u64, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "mlvae_reparam_kl_bwd": (_i, [_vp, _vp, _vp, _u64, _u64, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "mlvae_recon_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "mlvae_recon_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "mlvae_masked_reduce_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
@@ -44,6 +44,9 @@ SIGNATURES = {
     "mlvae_lstm_scratch_bytes": (_sz, [_i, _i]),
     "mlvae_lstm_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "mlvae_lstm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "mlvae_norm_state_bytes": (_sz, [_i]),
+    "mlvae_norm_scratch_bytes": (_sz, [_i, _i]),
+    "mlvae_global_norm": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp]),
     "mlvae_linear_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "mlvae_tc05_selftest": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "mlvae_fbank_fwd": (_i, [_vp, _vp, _vp, _i, _i64, _i64, _i, _vp, _i, _i, _vp, _vp, _vp]),

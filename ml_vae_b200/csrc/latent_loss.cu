@@ -188,9 +188,10 @@ template <typename T, int VEC> struct Chunk {   // VEC == Vec<T>::N (vector path
 template <typename T, int VEC>
 __global__ void __launch_bounds__(kThreads)
 reparam_kl_fwd_kernel(const T *__restrict__ mu, const T *__restrict__ logvar, const T *__restrict__ eps,
-                      uint64_t seed, uint64_t offset, const float *__restrict__ lens, int B, int Tn, int L,
+                      uint64_t seed, uint64_t offset, const uint64_t *__restrict__ offset_add, const float *__restrict__ lens, int B, int Tn, int L,
                       T *__restrict__ z, T *__restrict__ kl_elem, float *__restrict__ kl_out, ReduceScratch *scratch) {
     const PhiloxKey key(seed);
+    if (offset_add) offset += __ldg(offset_add);      // device-resident step counter (CUDA-graph friendly)
     float acc = 0.f;
     for (RowWalker w((int64_t)B * Tn, L / VEC, Tn); w.valid(); w.next()) {
         const int64_t e0 = w.vec * VEC;
@@ -220,11 +221,12 @@ reparam_kl_fwd_kernel(const T *__restrict__ mu, const T *__restrict__ logvar, co
 template <typename T, int VEC>
 __global__ void __launch_bounds__(kThreads)
 reparam_kl_bwd_kernel(const T *__restrict__ mu, const T *__restrict__ logvar, const T *__restrict__ eps,
-                      uint64_t seed, uint64_t offset, const T *__restrict__ grad_z,
+                      uint64_t seed, uint64_t offset, const uint64_t *__restrict__ offset_add, const T *__restrict__ grad_z,
                       const T *__restrict__ grad_kl_elem, const float *__restrict__ grad_kl_mean,
                       const float *__restrict__ lens, int B, int Tn, int L,
                       T *__restrict__ grad_mu, T *__restrict__ grad_logvar) {
     const PhiloxKey key(seed);
+    if (offset_add) offset += __ldg(offset_add);
     const float gscale = mean_grad_scale(grad_kl_mean, lens, B, Tn, L);
     for (RowWalker w((int64_t)B * Tn, L / VEC, Tn); w.valid(); w.next()) {
         const int64_t e0 = w.vec * VEC;
@@ -462,7 +464,7 @@ int mlvae_philox_normal(uint64_t seed, uint64_t offset, int64_t n, void *d_out, 
 }
 
 int mlvae_reparam_kl_fwd(const void *d_mu, const void *d_logvar, const void *d_eps, uint64_t seed, uint64_t offset,
-                         const float *d_lens, int B, int T_, int L, int dtype, void *d_z, void *d_kl_elem,
+                         const uint64_t *d_offset_add, const float *d_lens, int B, int T_, int L, int dtype, void *d_z, void *d_kl_elem,
                          float *d_kl_out, void *d_scratch, void *stream) {
     if (int rc = check_btc(B, T_, L)) return rc;
     MLVAE_REQUIRE(d_mu && d_logvar && d_z, MLVAE_ERR_INVALID_ARG, "reparam_kl_fwd: mu, logvar and z are required");
@@ -471,7 +473,7 @@ int mlvae_reparam_kl_fwd(const void *d_mu, const void *d_logvar, const void *d_e
     MLVAE_DISPATCH(dtype, L, al, {
         const int64_t nvec = (int64_t)B * T_ * (L / VEC);
         reparam_kl_fwd_kernel<T, VEC><<<grid_for(nvec), kThreads, 0, (cudaStream_t)stream>>>(
-            (const T *)d_mu, (const T *)d_logvar, (const T *)d_eps, seed, offset, d_lens, B, T_, L, (T *)d_z,
+            (const T *)d_mu, (const T *)d_logvar, (const T *)d_eps, seed, offset, d_offset_add, d_lens, B, T_, L, (T *)d_z,
             (T *)d_kl_elem, d_kl_out, (ReduceScratch *)d_scratch);
     });
     MLVAE_CHECK_CUDA(cudaGetLastError());
@@ -479,7 +481,7 @@ int mlvae_reparam_kl_fwd(const void *d_mu, const void *d_logvar, const void *d_e
 }
 
 int mlvae_reparam_kl_bwd(const void *d_mu, const void *d_logvar, const void *d_eps, uint64_t seed, uint64_t offset,
-                         const void *d_grad_z, const void *d_grad_kl_elem, const float *d_grad_kl_mean,
+                         const uint64_t *d_offset_add, const void *d_grad_z, const void *d_grad_kl_elem, const float *d_grad_kl_mean,
                          const float *d_lens, int B, int T_, int L, int dtype, void *d_grad_mu, void *d_grad_logvar,
                          void *stream) {
     if (int rc = check_btc(B, T_, L)) return rc;
@@ -490,7 +492,7 @@ int mlvae_reparam_kl_bwd(const void *d_mu, const void *d_logvar, const void *d_e
     MLVAE_DISPATCH(dtype, L, al, {
         const int64_t nvec = (int64_t)B * T_ * (L / VEC);
         reparam_kl_bwd_kernel<T, VEC><<<grid_for(nvec), kThreads, 0, (cudaStream_t)stream>>>(
-            (const T *)d_mu, (const T *)d_logvar, (const T *)d_eps, seed, offset, (const T *)d_grad_z,
+            (const T *)d_mu, (const T *)d_logvar, (const T *)d_eps, seed, offset, d_offset_add, (const T *)d_grad_z,
             (const T *)d_grad_kl_elem, d_grad_kl_mean, d_lens, B, T_, L, (T *)d_grad_mu, (T *)d_grad_logvar);
     });
     MLVAE_CHECK_CUDA(cudaGetLastError());

@@ -39,6 +39,7 @@ class VanillaVAE(nn.Module):
             attach(self, f"{head}.bias", b)
         self.seed = int(seed)
         self.calls = 0          # Philox offset: one fresh eps stream per forward
+        self.offset_dev = None  # optional device int64[1] step counter used INSTEAD of `calls` (CUDA-graph replays)
 
     def set_seed(self, seed: int, calls: int = 0):
         self.seed, self.calls = int(seed), int(calls)
@@ -61,10 +62,11 @@ class VanillaVAE(nn.Module):
 
     def forward(self, feats, lens=None, eps=None):
         mean, log_var = self.project(feats)
-        offset = self.calls
+        offset = 0 if self.offset_dev is not None else self.calls
         self.calls += 1
         z, kl_elem, kl_mean = ops.reparam_kl(mean, log_var, lens=lens, eps=eps, seed=self.seed, offset=offset,
-                                             want_elem=self.materialize_loss, want_mean=lens is not None)
+                                             want_elem=self.materialize_loss, want_mean=lens is not None,
+                                             offset_dev=self.offset_dev)
         out = {"mean": mean, "log_var": log_var, "sampled_h": z, "loss": kl_elem}
         if lens is not None:
             out["kld_loss"] = kl_mean

@@ -1,13 +1,14 @@
-"""Drop-in for ``speechbrain.processing.features.InputNormalization(norm_type='global')`` as
-declared at models/test_vanilla_vae/model.yaml:14-15 and called at
-models/test_vanilla_vae/model.py:24-25 [arithmetic: SB-recall, SpeechBrain 0.5.x]:
+"""Drop-in for ``speechbrain.processing.features.InputNormalization(norm_type='global')`` as declared at
+models/test_vanilla_vae/model.yaml:14-15 and called at models/test_vanilla_vae/model.py:24-25
+[arithmetic: SB-recall, SpeechBrain 0.5.x]:
 
-  per utterance: mean and unbiased std over the round(len * T) valid frames (std floored at
-  1e-10), averaged over the batch; running global statistics updated with weight
-  1 / (count + 1) while epoch < update_until_epoch (3); output (x - glob_mean) / glob_std.
+  per utterance: mean and unbiased std over the round(len * T) valid frames (std floored at 1e-10), averaged over
+  the batch; running global statistics updated with weight 1 / (count + 1) while epoch < update_until_epoch (3);
+  output (x - glob_mean) / glob_std.
 
-SpeechBrain loops over the batch in python with an .int() sync per utterance; this version is
-sync-free (statistics stay on the device) and batched.  SURVEY.md section 8f-2 ("next" row).
+SpeechBrain loops over the batch in python with an .int() sync per utterance; here three small kernels
+(csrc/norm.cu) do it with the running state (count, mean, std) resident on the device: no host sync, and the call is
+capturable in a CUDA graph.  SURVEY.md section 8f-2.
 """
 from __future__ import annotations
 
@@ -24,34 +25,42 @@ class InputNormalization(torch.nn.Module):
             raise NotImplementedError("only InputNormalization(norm_type='global') with SpeechBrain defaults "
                                       "(the reference's configuration, model.yaml:14-15) is implemented")
         self.update_until_epoch = update_until_epoch
-        self.eps = 1e-10
-        self.count = 0
-        self.register_buffer("glob_mean", torch.zeros(0), persistent=False)
-        self.register_buffer("glob_std", torch.zeros(0), persistent=False)
+        self._state = None          # {count, pad[3], glob_mean[D], glob_std[D]} float32 on the device
+        self._scratch = None
+        self._dim = None
+
+    # running statistics, as views of the device state
+    @property
+    def count(self) -> int:
+        return 0 if self._state is None else int(self._state[0].item())
+
+    @property
+    def glob_mean(self):
+        return None if self._state is None else self._state[4:4 + self._dim]
+
+    @property
+    def glob_std(self):
+        return None if self._state is None else self._state[4 + self._dim:4 + 2 * self._dim]
 
     @torch.no_grad()
-    def batch_stats(self, x: torch.Tensor, lens: torch.Tensor):
-        B, T, D = x.shape
-        n = torch.round(lens.to(x.device).float() * T).clamp_(min=0, max=T)            # (B,)
-        m = (torch.arange(T, device=x.device)[None, :] < n[:, None]).to(torch.float32)[..., None]
-        xf = x.float()
-        mean = (xf * m).sum(1) / n[:, None]
-        var = (((xf - mean[:, None, :]) * m) ** 2).sum(1) / (n[:, None] - 1)
-        std = var.sqrt().clamp_(min=self.eps)
-        return mean.mean(0), std.mean(0)
-
-    @torch.no_grad()
-    def forward(self, x, lengths, epoch=0):
+    def forward(self, x, lengths, epoch=0, out_dtype=None):
         L.require_cuda(x)
-        if self.training:
-            cm, cs = self.batch_stats(x, lengths)
-            if self.count == 0:
-                self.glob_mean, self.glob_std = cm, cs
-            elif epoch < self.update_until_epoch:
-                w = 1.0 / (self.count + 1)
-                self.glob_mean = (1 - w) * self.glob_mean + w * cm
-                self.glob_std = (1 - w) * self.glob_std + w * cs
-            self.count += 1
-        elif self.count == 0:
+        if x.dim() != 3:
+            raise ValueError(f"expected (batch, time, features), got {tuple(x.shape)}")
+        B, T, D = x.shape
+        xf = x.float().contiguous()
+        lens = lengths.to(device=x.device, dtype=torch.float32).contiguous()
+        if self._state is None or self._dim != D or self._state.device != x.device:
+            self._state = torch.zeros(L.lib().mlvae_norm_state_bytes(D) // 4, dtype=torch.float32, device=x.device)
+            self._dim = D
+        need = L.lib().mlvae_norm_scratch_bytes(B, D) // 4
+        if self._scratch is None or self._scratch.numel() < need or self._scratch.device != x.device:
+            self._scratch = torch.empty(need, dtype=torch.float32, device=x.device)
+        out = torch.empty(B, T, D, dtype=out_dtype or x.dtype, device=x.device)
+        if not self.training and self.count == 0:
             raise RuntimeError("InputNormalization(global) used in eval mode before any statistics were seen")
-        return ((x.float() - self.glob_mean) / self.glob_std).to(x.dtype)
+        L.check(L.lib().mlvae_global_norm(L.ptr(xf), L.ptr(lens), B, T, D, int(self.training),
+                                          int(epoch < self.update_until_epoch), L.ptr(self._state), L.ptr(self._scratch),
+                                          L.ptr(out), L.dtype_code(out), L.stream_ptr()), "mlvae_global_norm",
+                kernels=3 if self.training else 1)
+        return out

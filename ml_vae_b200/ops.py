@@ -49,7 +49,7 @@ def philox_u32(n: int, seed: int, offset: int = 0, device="cuda") -> torch.Tenso
 
 class _ReparamKL(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, mu, logvar, eps, lens, seed, offset, want_elem, want_mean):
+    def forward(ctx, mu, logvar, eps, lens, seed, offset, want_elem, want_mean, offset_dev=None):
         L.require_cuda(mu, logvar, eps)
         if mu.shape != logvar.shape or mu.dtype != logvar.dtype:
             raise ValueError("mean and log_var must have the same shape and dtype")
@@ -64,11 +64,11 @@ class _ReparamKL(torch.autograd.Function):
         if want_mean and lens_f is None:
             raise ValueError("reduced KL needs lens")
         L.check(L.lib().mlvae_reparam_kl_fwd(
-            L.ptr(mu), L.ptr(logvar), L.ptr(eps), seed, offset, L.ptr(lens_f), B, T, C, L.dtype_code(mu),
+            L.ptr(mu), L.ptr(logvar), L.ptr(eps), seed, offset, L.ptr(offset_dev), L.ptr(lens_f), B, T, C, L.dtype_code(mu),
             L.ptr(z), L.ptr(kl_elem), L.ptr(kl_out), L.ptr(L.reduce_scratch(mu.device)) if want_mean else None,
             L.stream_ptr()), "mlvae_reparam_kl_fwd")
         ctx.save_for_backward(mu, logvar, eps, lens_f)
-        ctx.seed, ctx.offset = seed, offset
+        ctx.seed, ctx.offset, ctx.offset_dev = seed, offset, offset_dev
         ctx.set_materialize_grads(False)
         empty = mu.new_empty(0)
         return z, (kl_elem if want_elem else empty), (kl_out[0] if want_mean else empty.float())
@@ -84,15 +84,16 @@ class _ReparamKL(torch.autograd.Function):
             gz = gz.to(mu.dtype)
         gmu, glv = torch.empty_like(mu), torch.empty_like(mu)
         L.check(L.lib().mlvae_reparam_kl_bwd(
-            L.ptr(mu), L.ptr(logvar), L.ptr(eps), ctx.seed, ctx.offset, L.ptr(gz), L.ptr(gelem), L.ptr(gmean),
+            L.ptr(mu), L.ptr(logvar), L.ptr(eps), ctx.seed, ctx.offset, L.ptr(ctx.offset_dev), L.ptr(gz), L.ptr(gelem), L.ptr(gmean),
             L.ptr(lens_f), B, T, C, L.dtype_code(mu), L.ptr(gmu), L.ptr(glv), L.stream_ptr()), "mlvae_reparam_kl_bwd")
-        return gmu, glv, None, None, None, None, None, None
+        return gmu, glv, None, None, None, None, None, None, None
 
 
 def reparam_kl(mu, logvar, lens=None, eps=None, seed: int = 0, offset: int = 0,
-               want_elem: bool = False, want_mean: bool = True):
-    """-> (z, kl_elem | None, kl_mean | None).  eps=None draws Philox(seed, offset)."""
-    z, e, m = _ReparamKL.apply(mu, logvar, eps, lens, int(seed), int(offset), want_elem, want_mean)
+               want_elem: bool = False, want_mean: bool = True, offset_dev=None):
+    """-> (z, kl_elem | None, kl_mean | None).  eps=None draws Philox(seed, offset [+ offset_dev[0], a device
+    int64 step counter that keeps CUDA-graph replays drawing fresh noise])."""
+    z, e, m = _ReparamKL.apply(mu, logvar, eps, lens, int(seed), int(offset), want_elem, want_mean, offset_dev)
     return z, (e if want_elem else None), (m if want_mean else None)
 
 
@@ -118,7 +119,6 @@ class _ReconLoss(torch.autograd.Function):
             "mlvae_recon_fwd")
         ctx.save_for_backward(mean, logvar, target, lens_f)
         ctx.loss_type = loss_type
-        ctx.need_target = target.requires_grad
         ctx.set_materialize_grads(False)
         empty = mean.new_empty(0)
         return (elem if want_elem else empty), (out[0] if want_mean else empty.float())

@@ -93,11 +93,16 @@ class TrainStep:
         self.decoder.materialize_loss = False
         self.found_inf = torch.zeros((), dtype=torch.float32, device=self.arena.flat.device)
         self.last = {}
+        # device-resident step counter = Philox offset of the reparameterisation noise: a captured CUDA graph then
+        # draws fresh eps on every replay
+        self.step_counter = torch.zeros(1, dtype=torch.int64, device=self.arena.flat.device)
+        self.encoder.offset_dev = self.step_counter
+        self._graph = None
 
     # -- forward pieces -------------------------------------------------------------------
     def features(self, wav, wav_lens):
         feats, rel = self.fbank(wav, wav_lens, truncate=True, out_dtype=torch.float32)
-        return self.normalizer(feats, rel, epoch=self.epoch).to(self.dtype), rel
+        return self.normalizer(feats, rel, epoch=self.epoch, out_dtype=self.dtype), rel
 
     def losses(self, feats, rel):
         eo = self.encoder(feats, lens=rel)
@@ -116,10 +121,48 @@ class TrainStep:
         self.opt.grad_scale, self.opt.found_inf = None, self.found_inf
         self.opt.step()
         self.arena.zero_grad()
+        self.step_counter += 1
         self.last = {"loss": loss.detach(), "kld_loss": kld.detach(), "recon_loss": rec.detach()}
         return self.last["loss"]
 
-    def step(self, wav, wav_lens):
-        """wav (B, N) float32 on the device, wav_lens (B,) absolute samples or relative lengths."""
+    def _step_eager(self, wav, wav_lens):
         feats, rel = self.features(wav, wav_lens)
         return self.step_from_features(feats, rel)
+
+    def step(self, wav, wav_lens):
+        """wav (B, N) float32 on the device, wav_lens (B,) absolute samples or relative lengths."""
+        if self._graph is not None and wav.shape == self._g_wav.shape:
+            self._g_wav.copy_(wav, non_blocking=True)
+            self._g_lens.copy_(wav_lens.to(self._g_lens.dtype), non_blocking=True)
+            self._graph.replay()
+            return self.last["loss"]
+        return self._step_eager(wav, wav_lens)
+
+    # -- CUDA graph ---------------------------------------------------------------------------
+    def capture(self, wav, wav_lens, warmup: int = 3) -> bool:
+        """Capture the whole step (front-end, forward, backward, all-reduce, clip, Adam) for this input shape in
+        one CUDA graph; later ``step`` calls with the same shape replay it.  All per-step state that used to live
+        on the host (Philox offset, normaliser count, non-finite skip) is device resident, so replays are real
+        training steps.  ``warmup`` eager steps run first (they are training steps too).  Returns False and stays
+        eager if capture is refused (e.g. by the communicator)."""
+        self._g_wav = wav.clone()
+        self._g_lens = wav_lens.clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        try:
+            with torch.cuda.stream(side):
+                for _ in range(warmup):
+                    self._step_eager(self._g_wav, self._g_lens)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._step_eager(self._g_wav, self._g_lens)
+            self._graph = graph
+            return True
+        except Exception as exc:                       # stay correct: fall back to eager stepping
+            import warnings
+            warnings.warn(f"CUDA-graph capture of the training step failed, staying eager: {exc}")
+            self._graph = None
+            torch.cuda.synchronize()
+            return False

@@ -33,7 +33,7 @@ def test_cabi_argument_validation_without_gpu(lib_built):
     """Entry points validate before touching the device: bad arguments give negative status + text."""
     from ml_vae_b200 import _lib as L
     lib = L.lib()
-    assert lib.mlvae_reparam_kl_fwd(None, None, None, 0, 0, None, 1, 1, 1, 0, None, None, None, None, None) == -1
+    assert lib.mlvae_reparam_kl_fwd(None, None, None, 0, 0, None, None, 1, 1, 1, 0, None, None, None, None, None) == -1
     assert b"required" in lib.mlvae_last_error()
     assert lib.mlvae_recon_fwd(None, None, None, None, 1, 1, 1, 0, 7, None, None, None, None) == -1
     assert b"Invalid loss type" in lib.mlvae_last_error()

@@ -129,3 +129,55 @@ def test_train_step_bf16_learns_and_skips_nonfinite(cuda):
     ts.step(bad, lens)                                   # non-finite loss: update skipped on the device
     assert not torch.isfinite(ts.last["loss"])
     assert torch.equal(ts.arena.flat, before)
+
+
+def test_normalizer_kernel_matches_oracle(cuda):
+    """InputNormalization(global) on csrc/norm.cu vs the oracle restatement, over several batches/epochs
+    (first batch initialises, running average with weight 1/(count+1), frozen from epoch 3 on)."""
+    from ml_vae_b200.normalizer import InputNormalization
+    g = torch.Generator().manual_seed(9)
+    ours, ref = InputNormalization().to(cuda), vae_ref.GlobalNormRef()
+    for it, epoch in enumerate([0, 0, 1, 2, 3, 5]):
+        B, T, D = 5, 37 + it, 24
+        x = torch.randn(B, T, D, generator=g) * (1 + it) + it
+        n = torch.randint(2, T + 1, (B,), generator=g)
+        n[0] = T
+        lens = n.float() / T
+        want = ref(x, lens, epoch=epoch)
+        got = ours(x.to(cuda), lens.to(cuda), epoch=epoch)
+        assert_close(got, want, FP32_RTOL, f"batch {it}")
+    assert ours.count == ref.count
+    assert_close(ours.glob_std, ref.glob_std, FP32_RTOL, "running std")
+    b16 = ours(x.to(cuda), lens.to(cuda), epoch=9, out_dtype=torch.bfloat16)
+    assert b16.dtype == torch.bfloat16
+
+
+def test_train_step_cuda_graph_replays_are_training_steps(cuda):
+    """Captured step == eager step: same losses step by step (fresh eps each replay through the device counter,
+    device-resident normaliser state, Adam)."""
+    from ml_vae_b200.features import Fbank
+    from ml_vae_b200.modules import Decoder, VanillaVAE
+    from ml_vae_b200.normalizer import InputNormalization
+    from ml_vae_b200.train_step import TrainStep
+
+    def make():
+        torch.manual_seed(11)
+        enc = VanillaVAE([80, 64, 64], 64).to(cuda)
+        dec = Decoder(64, 64, 2, 0.0, [128, 64, 64, 80]).to(cuda)
+        return TrainStep(Fbank(deltas=False, hop_length=10, n_mels=80), InputNormalization().to(cuda), enc, dec,
+                         {"kld_weight": 0.001, "batch_size": 8}, compute_dtype=torch.bfloat16, seed=5)
+
+    g = torch.Generator().manual_seed(2)
+    batches = [(0.1 * torch.randn(8, 8000, generator=g)).to(cuda) for _ in range(3)]
+    lens = torch.full((8,), 8000, dtype=torch.int32, device=cuda)
+    eager, graphed = make(), make()
+    assert graphed.capture(batches[0], lens, warmup=2)
+    for _ in range(2):                                                     # the capture ran 2 eager warm-up steps
+        eager.step(batches[0], lens)
+    seq_e, seq_g = [], []
+    for i in range(6):
+        seq_e.append(float(eager.step(batches[i % 3], lens)))
+        seq_g.append(float(graphed.step(batches[i % 3], lens)))
+    assert int(graphed.step_counter) == int(eager.step_counter)
+    assert np.allclose(seq_e, seq_g, rtol=2e-2), (seq_e, seq_g)
+    assert len(set(seq_g)) == len(seq_g)                                   # not a frozen replay
