@@ -211,7 +211,6 @@ def run_ours(args):
     host = [(0.1 * torch.randn(B, n, generator=g)).pin_memory() for _ in range(R)]
     resident = [h.to(dev) for h in host]
     lens_abs = torch.full((B,), n, dtype=torch.int32, device=dev)
-    stage = torch.empty(B, n, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def barrier():
@@ -240,8 +239,14 @@ def run_ours(args):
         ts.step(resident[i % R], lens_abs)
 
     def step_e2e(i):
-        stage.copy_(host[i % R], non_blocking=True)             # H2D of this step's input, pinned
-        loss = ts.step(stage, lens_abs)
+        # public API a data loader would drive: every step's waveforms come from pinned HOST memory.  The copy of batch
+        # i+1 is issued before the loss of step i is read back, so it streams over PCIe while step i computes; all
+        # `steps` copies happen inside the timed regions (the first one un-overlapped, at the head of step 0).
+        if not ts.__dict__.get("_pending"):
+            ts.submit_host_batch(host[i % R])
+        loss = ts.step_submitted(lens_abs)
+        if i + 1 < e2e_steps[0]:
+            ts.submit_host_batch(host[(i + 1) % R])
         return float(loss.cpu())                                # D2H read of the step's result
 
     sampler = ClockSampler(local)
@@ -285,23 +290,28 @@ def run_ours(args):
     # step is captured the probe runs on 3 extra EAGER steps of the same step function right after the timed region.
     probe_steps = args.steps
     if graphed:
+        ts._step_eager(resident[0], lens_abs)          # untimed: first eager step after the capture re-grows the allocator
+        torch.cuda.synchronize()
         L.LAUNCHES = 0
         fb_evs.clear()
         lstm_mod.PROBE = []
-        probe_steps = 3
+        probe_steps = 4
         for i in range(probe_steps):
             ts._step_eager(resident[i % R], lens_abs)
         torch.cuda.synchronize()
     launches = getattr(L, "LAUNCHES", 0) * (args.steps / probe_steps)
     ts.features = orig_features
-    fb_ms = sum(a.elapsed_time(b) for a, b in fb_evs) / max(len(fb_evs), 1)
+    fb_all = sorted(a.elapsed_time(b) for a, b in fb_evs)
+    fb_ms = fb_all[len(fb_all) // 2] if fb_all else float('nan')          # median launch
     lstm_ms = {}
     for tag, a, b in lstm_mod.PROBE:
         lstm_ms.setdefault(tag, []).append(a.elapsed_time(b))
     lstm_mod.PROBE = None
 
-    for i in range(max(1, args.warmup // 2)):
+    e2e_steps = [max(1, args.warmup // 2)]
+    for i in range(e2e_steps[0]):
         step_e2e(i)
+    e2e_steps[0] = args.steps
     sec_e2e, _ = timed(step_e2e, args.steps)
 
     value = B * world * args.steps / sec

@@ -138,6 +138,34 @@ class TrainStep:
             return self.last["loss"]
         return self._step_eager(wav, wav_lens)
 
+    # -- host-fed stepping with the H2D copy of the next batch overlapped --------------------------
+    def submit_host_batch(self, host_wav: torch.Tensor):
+        """Start copying a (pinned) host batch to the device on a side stream; consumed by the next
+        ``step_submitted``.  Two staging buffers: batch i+1 streams in over PCIe while step i computes."""
+        if getattr(self, "_copy_stream", None) is None:
+            dev = self.arena.flat.device
+            self._copy_stream = torch.cuda.Stream(dev)
+            self._stage = [torch.empty(host_wav.shape, dtype=torch.float32, device=dev) for _ in range(2)]
+            self._ready = [torch.cuda.Event() for _ in range(2)]
+            self._free = [torch.cuda.Event() for _ in range(2)]
+            for e in self._free:
+                e.record()
+            self._pf, self._pending = 0, []
+        k = self._pf
+        self._copy_stream.wait_event(self._free[k])            # the step that last read this buffer has finished
+        with torch.cuda.stream(self._copy_stream):
+            self._stage[k].copy_(host_wav, non_blocking=True)
+            self._ready[k].record(self._copy_stream)
+        self._pending.append(k)
+        self._pf ^= 1
+
+    def step_submitted(self, wav_lens):
+        k = self._pending.pop(0)
+        torch.cuda.current_stream().wait_event(self._ready[k])
+        loss = self.step(self._stage[k], wav_lens)
+        self._free[k].record()
+        return loss
+
     # -- CUDA graph ---------------------------------------------------------------------------
     def capture(self, wav, wav_lens, warmup: int = 3) -> bool:
         """Capture the whole step (front-end, forward, backward, all-reduce, clip, Adam) for this input shape in
