@@ -89,11 +89,11 @@ def main():
                 st = L.stream_ptr()
 
                 def fwd():
-                    L.check(lib.mlvae_reparam_kl_fwd(L.ptr(mu), L.ptr(lv), None, 1, 0, L.ptr(lens), B, T, Ld, code,
+                    L.check(lib.mlvae_reparam_kl_fwd(L.ptr(mu), L.ptr(lv), None, 1, 0, None, L.ptr(lens), B, T, Ld, code,
                                                      L.ptr(z), None, L.ptr(out), L.ptr(sc), st))
 
                 def bwd():
-                    L.check(lib.mlvae_reparam_kl_bwd(L.ptr(mu), L.ptr(lv), None, 1, 0, L.ptr(gz), None, L.ptr(one),
+                    L.check(lib.mlvae_reparam_kl_bwd(L.ptr(mu), L.ptr(lv), None, 1, 0, None, L.ptr(gz), None, L.ptr(one),
                                                      L.ptr(lens), B, T, Ld, code, L.ptr(gmu), L.ptr(glv), st))
 
                 big = M * Ld * s * 3 > (200 << 20)

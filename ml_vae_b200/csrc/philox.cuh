@@ -34,7 +34,10 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, const PhiloxKey &key) {
 __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float &n0, float &n1) {
     const float u1 = (__uint2float_rn(a) + 1.0f) * 2.3283064365386963e-10f;
     const float th = __int2float_rn((int)b) * 1.4629180792671596e-9f;
-    const float r = sqrtf(-2.0f * __logf(u1));
+    // sqrt.approx (MUFU): the IEEE sqrtf costs ~10 extra instructions and a divergent slow path per call; u1 in (0, 1]
+    // keeps the argument in [0, 44.4], sqrt.approx.ftz(+0) = +0
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-2.0f * __logf(u1)));
     float s, c;
     __sincosf(th, &s, &c);
     n0 = r * c;
