@@ -476,15 +476,19 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_bwd_kernel(LstmBwdParams
         PROF_MARK(2);                                   // MMA
         // ---- phase C (producer side): ship partials to the owners of units jh ----
         uint2 *dst = p.ll + ((size_t)((step + 1) & 1) * groups + group) * ll_words;
-        for (int m = 0; m < tiles; ++m) {
-            uint32_t v[CPW];
-            tc::tmem_ld<CPW>(tmem + lane_base + dcol + m * NB + part * CPW, v);
-            tc::tmem_ld_wait();
+        constexpr int kMaxTiles = 4;                     // H <= 512
+        uint32_t v[kMaxTiles][CPW];
+#pragma unroll
+        for (int m = 0; m < kMaxTiles; ++m)              // all TMEM loads in flight, ONE wait
+            if (m < tiles) tc::tmem_ld<CPW>(tmem + lane_base + dcol + m * NB + part * CPW, v[m]);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int m = 0; m < kMaxTiles; ++m) {
             const int owner = 4 * m + q;                 // CTA that owns unit jh = 128 m + 32 q + lane
-            if (owner < G) {
+            if (m < tiles && owner < G) {
 #pragma unroll
                 for (int e = 0; e < CPW / 2; ++e) {
-                    const __nv_bfloat162 pk = __floats2bfloat162_rn(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]));
+                    const __nv_bfloat162 pk = __floats2bfloat162_rn(__uint_as_float(v[m][2 * e]), __uint_as_float(v[m][2 * e + 1]));
                     const int jp = part * (CPW / 2) + e;
                     st_volatile_u2(dst + (((size_t)owner * G + u) * (NB / 2) + jp) * 32 + lane,
                                    make_uint2(*reinterpret_cast<const uint32_t *>(&pk), (uint32_t)(step + 1)));
