@@ -20,7 +20,8 @@ LEAKY_SLOPE = 0.01
 
 
 def _tc_ok(x2: torch.Tensor, n_out: int, k_in: int) -> bool:
-    return x2.dtype == torch.bfloat16 and n_out <= 256 and k_in % 8 == 0 and x2.stride(0) % 8 == 0
+    return (x2.dtype == torch.bfloat16 and n_out <= 256 and k_in % 8 == 0 and x2.stride(0) % 8 == 0
+            and x2.data_ptr() % 16 == 0)
 
 
 def _launch(x2, w_bf16, bias_f32, n_out, leaky):
@@ -64,7 +65,7 @@ def linear(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, leaky: bool = Fals
     lead = x.shape[:-1]
     x2 = x.reshape(-1, x.shape[-1])
     if _tc_ok(x2, w.shape[0], w.shape[1]):
-        y = _LinearTC.apply(x2.contiguous(), w, b, leaky)
+        y = _LinearTC.apply(x2 if x2.stride(1) == 1 else x2.contiguous(), w, b, leaky)
     else:
         y = F.linear(x2, w.to(x.dtype), b.to(x.dtype))
         if leaky:

@@ -16,7 +16,7 @@ import torch
 from torch import nn
 
 from .. import lstm, ops
-from ..dense import linear_chain
+from ..dense import linear, linear_chain
 from ._params import attach, torch_default_linear, torch_default_lstm
 
 
@@ -69,8 +69,17 @@ class Decoder(nn.Module):
         if self.loss_type not in ("likelihood", "mse"):
             raise ValueError(f"Invalid loss type: {self.loss_type}")
         rnn_out = self.run_rnn(sampled_h)
-        mean = linear_chain(rnn_out, *self._head("mean_fc"))
-        log_var = linear_chain(rnn_out, *self._head("log_var_fc"))
+        (wm, bm), (wv, bv) = self._head("mean_fc"), self._head("log_var_fc")
+        if len(wm) > 1 and wm[0].shape == wv[0].shape:
+            # both heads read the (B, T, 2H) LSTM output: their first layers run as ONE GEMM against the stacked
+            # weight, so the widest activation of the model is read once (decoder.py:24-25 reads it twice)
+            n0 = wm[0].shape[0]
+            h0 = linear(rnn_out, torch.cat([wm[0], wv[0]], 0), torch.cat([bm[0], bv[0]], 0), leaky=True)
+            mean = linear_chain(h0[..., :n0], wm[1:], bm[1:])
+            log_var = linear_chain(h0[..., n0:], wv[1:], bv[1:])
+        else:
+            mean = linear_chain(rnn_out, wm, bm)
+            log_var = linear_chain(rnn_out, wv, bv)
         elem, red = ops.recon_loss(mean, log_var, target_feats, lens=lens, loss_type=self.loss_type,
                                    want_elem=self.materialize_loss, want_mean=lens is not None)
         out = {"mean": mean, "log_var": log_var, "losses": {"recon_loss": elem}}
