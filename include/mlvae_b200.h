@@ -128,6 +128,27 @@ int mlvae_recon_bwd(const void *d_mean, const void *d_logvar, const void *d_targ
                     void *d_grad_mean, void *d_grad_logvar, void *d_grad_target, void *stream);
 
 /* ------------------------------------------------------------------------- *
+ * GMM-VAE / hierarchical-VAE family.
+ * mlvae_gmm_reparam_kl_*: GMMVAE.reparameterize + compute_kld_loss against a LEARNED prior
+ *   (modules/gmm_vae.py:51-67), unreduced, flat over n elements (n = B*T*N*L):
+ *     z  = mu + exp(0.5*logvar) * eps
+ *     kl = -0.5 * (1 + logvar - plogvar - (exp(logvar) + (mu - pmu)^2) / (exp(plogvar) + 1e-5))
+ * mlvae_apply_weight_*: utils/data_utils.py:32-64 apply_weight(x (M,N,C), w (M,N)) -> (M,C), used 8x per
+ *   HierarchicalVAE.forward (modules/h_vae.py:45-60); the backward gives both grad_x and grad_w (the
+ *   straight-through Gumbel-softmax gradient flows through w).
+ * ------------------------------------------------------------------------- */
+int mlvae_gmm_reparam_kl_fwd(const void *d_mu, const void *d_logvar, const void *d_prior_mu, const void *d_prior_logvar,
+                             const void *d_eps, uint64_t seed, uint64_t offset, const uint64_t *d_offset_add, int64_t n,
+                             int dtype, void *d_z, void *d_kl_elem, void *stream);
+int mlvae_gmm_reparam_kl_bwd(const void *d_mu, const void *d_logvar, const void *d_prior_mu, const void *d_prior_logvar,
+                             const void *d_eps, uint64_t seed, uint64_t offset, const uint64_t *d_offset_add,
+                             const void *d_grad_z, const void *d_grad_kl_elem, int64_t n, int dtype, void *d_grad_mu,
+                             void *d_grad_logvar, void *d_grad_prior_mu, void *d_grad_prior_logvar, void *stream);
+int mlvae_apply_weight_fwd(const void *d_x, const void *d_w, int64_t M, int N, int C, int dtype, void *d_out, void *stream);
+int mlvae_apply_weight_bwd(const void *d_x, const void *d_w, const void *d_grad_out, int64_t M, int N, int C, int dtype,
+                           void *d_grad_x, void *d_grad_w, void *stream);
+
+/* ------------------------------------------------------------------------- *
  * Stand-alone length-masked reduction = utils/data_utils.py:67-104
  * apply_lens_to_loss(loss (B,T,C), lens (B,), reduction) for callers that keep
  * the reference's unreduced-loss module contract.

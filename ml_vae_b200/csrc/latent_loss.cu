@@ -388,6 +388,111 @@ masked_reduce_bwd_kernel(const float *__restrict__ grad_out, const float *__rest
     }
 }
 
+// ------------------------------------ GMM-VAE reparameterise + KL vs a learned prior ------
+// modules/gmm_vae.py:51-67: z = mu + exp(0.5 lv) eps ;
+// kl = -0.5 (1 + lv - plv - (exp(lv) + (mu - pmu)^2) / (exp(plv) + 1e-5)), unreduced (the mixing by
+// gmm_weight / pi that follows needs it per element).  Flat elementwise, 16-byte vectors.
+constexpr float kGmmEps = 1e-5f;
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kThreads)
+gmm_reparam_kl_fwd_kernel(const T *__restrict__ mu, const T *__restrict__ logvar, const T *__restrict__ pmu,
+                          const T *__restrict__ plogvar, const T *__restrict__ eps, uint64_t seed, uint64_t offset,
+                          const uint64_t *__restrict__ offset_add, int64_t n, T *__restrict__ z, T *__restrict__ kl) {
+    const PhiloxKey key(seed);
+    if (offset_add) offset += __ldg(offset_add);
+    const int64_t nvec = n / VEC;
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e0 = v * VEC;
+        Chunk<T, VEC> m, lv, pm, plv, ep, zz, kk;
+        m.load(mu + e0); lv.load(logvar + e0); pm.load(pmu + e0); plv.load(plogvar + e0);
+        if (eps) ep.load(eps + e0);
+        else stream_eps<VEC>(e0, offset, key, ep.v);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            const float sd = fast_exp<T>(0.5f * lv.v[i]);
+            zz.v[i] = fmaf(ep.v[i], sd, m.v[i]);
+            const float d = m.v[i] - pm.v[i];
+            kk.v[i] = -0.5f * (1.f + lv.v[i] - plv.v[i] - (sd * sd + d * d) / (fast_exp<T>(plv.v[i]) + kGmmEps));
+        }
+        zz.store(z + e0);
+        kk.store(kl + e0);
+    }
+}
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kThreads)
+gmm_reparam_kl_bwd_kernel(const T *__restrict__ mu, const T *__restrict__ logvar, const T *__restrict__ pmu,
+                          const T *__restrict__ plogvar, const T *__restrict__ eps, uint64_t seed, uint64_t offset,
+                          const uint64_t *__restrict__ offset_add, const T *__restrict__ grad_z, const T *__restrict__ grad_kl,
+                          int64_t n, T *__restrict__ g_mu, T *__restrict__ g_lv, T *__restrict__ g_pmu, T *__restrict__ g_plv) {
+    const PhiloxKey key(seed);
+    if (offset_add) offset += __ldg(offset_add);
+    const int64_t nvec = n / VEC;
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e0 = v * VEC;
+        Chunk<T, VEC> m, lv, pm, plv, ep, gz, gk, om, ol, opm, opl;
+        m.load(mu + e0); lv.load(logvar + e0); pm.load(pmu + e0); plv.load(plogvar + e0);
+        if (grad_z) gz.load(grad_z + e0); else gz.zero();
+        if (grad_kl) gk.load(grad_kl + e0); else gk.zero();
+        if (eps) ep.load(eps + e0);
+        else stream_eps<VEC>(e0, offset, key, ep.v);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            const float sd = fast_exp<T>(0.5f * lv.v[i]);
+            const float e = sd * sd, ep_ = fast_exp<T>(plv.v[i]);
+            const float inv = 1.f / (ep_ + kGmmEps);
+            const float d = m.v[i] - pm.v[i];
+            const float g = gk.v[i];
+            om.v[i] = fmaf(g, d * inv, gz.v[i]);
+            opm.v[i] = -g * d * inv;
+            ol.v[i] = fmaf(gz.v[i] * 0.5f * sd, ep.v[i], -0.5f * g * (1.f - e * inv));
+            opl.v[i] = 0.5f * g * (1.f - (e + d * d) * ep_ * inv * inv);
+        }
+        om.store(g_mu + e0); ol.store(g_lv + e0); opm.store(g_pmu + e0); opl.store(g_plv + e0);
+    }
+}
+
+// --------------------------------------------------- apply_weight (utils/data_utils.py:32-64) ------
+// out[m, c] = sum_n w[m, n] * x[m, n, c]; the reference runs M tiny (1 x N) @ (N x C) bmm problems.
+// One warp per row m, lanes over c.
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+apply_weight_fwd_kernel(const T *__restrict__ x, const T *__restrict__ w, int64_t M, int N, int C, T *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t m = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); m < M; m += warps) {
+        const T *xm = x + m * N * C;
+        for (int c = lane; c < C; c += 32) {
+            float acc = 0.f;
+            for (int nn = 0; nn < N; ++nn) acc = fmaf(to_f32<T>(w[m * N + nn]), to_f32<T>(xm[(int64_t)nn * C + c]), acc);
+            out[m * C + c] = from_f32<T>(acc);
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+apply_weight_bwd_kernel(const T *__restrict__ x, const T *__restrict__ w, const T *__restrict__ g, int64_t M, int N, int C,
+                        T *__restrict__ gx, T *__restrict__ gw) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t m = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); m < M; m += warps) {
+        const T *xm = x + m * N * C;
+        for (int nn = 0; nn < N; ++nn) {
+            const float wn = to_f32<T>(w[m * N + nn]);
+            float dot = 0.f;
+            for (int c = lane; c < C; c += 32) {
+                const float gc = to_f32<T>(g[m * C + c]);
+                if (gx) gx[(m * N + nn) * C + c] = from_f32<T>(wn * gc);
+                dot = fmaf(to_f32<T>(xm[(int64_t)nn * C + c]), gc, dot);
+            }
+            dot = warp_sum(dot);
+            if (gw && lane == 0) gw[m * N + nn] = from_f32<T>(dot);
+        }
+    }
+}
+
 // ------------------------------------------------------------ launching ----
 inline int grid_for(int64_t nvec, int ctas_per_sm = 8) {
     int64_t g = (nvec + kThreads - 1) / kThreads;
@@ -549,6 +654,62 @@ int mlvae_recon_bwd(const void *d_mean, const void *d_logvar, const void *d_targ
                 (const T *)d_mean, (const T *)d_logvar, (const T *)d_target, (const T *)d_grad_elem, d_grad_mean_scalar,
                 d_lens, B, T_, D, (T *)d_grad_mean, (T *)d_grad_logvar, (T *)d_grad_target);
     });
+    MLVAE_CHECK_CUDA(cudaGetLastError());
+    return MLVAE_OK;
+}
+
+int mlvae_gmm_reparam_kl_fwd(const void *d_mu, const void *d_logvar, const void *d_prior_mu, const void *d_prior_logvar,
+                             const void *d_eps, uint64_t seed, uint64_t offset, const uint64_t *d_offset_add, int64_t n,
+                             int dtype, void *d_z, void *d_kl_elem, void *stream) {
+    MLVAE_REQUIRE(d_mu && d_logvar && d_prior_mu && d_prior_logvar && d_z && d_kl_elem && n > 0, MLVAE_ERR_INVALID_ARG,
+                  "gmm_reparam_kl_fwd: missing buffers");
+    const bool al = aligned16(d_mu) && aligned16(d_logvar) && aligned16(d_prior_mu) && aligned16(d_prior_logvar) &&
+                    aligned16(d_eps) && aligned16(d_z) && aligned16(d_kl_elem);
+    MLVAE_DISPATCH(dtype, n, al, {
+        gmm_reparam_kl_fwd_kernel<T, VEC><<<grid_for(n / VEC), kThreads, 0, (cudaStream_t)stream>>>(
+            (const T *)d_mu, (const T *)d_logvar, (const T *)d_prior_mu, (const T *)d_prior_logvar, (const T *)d_eps, seed, offset,
+            d_offset_add, n, (T *)d_z, (T *)d_kl_elem);
+    });
+    MLVAE_CHECK_CUDA(cudaGetLastError());
+    return MLVAE_OK;
+}
+
+int mlvae_gmm_reparam_kl_bwd(const void *d_mu, const void *d_logvar, const void *d_prior_mu, const void *d_prior_logvar,
+                             const void *d_eps, uint64_t seed, uint64_t offset, const uint64_t *d_offset_add,
+                             const void *d_grad_z, const void *d_grad_kl_elem, int64_t n, int dtype, void *d_grad_mu,
+                             void *d_grad_logvar, void *d_grad_prior_mu, void *d_grad_prior_logvar, void *stream) {
+    MLVAE_REQUIRE(d_mu && d_logvar && d_prior_mu && d_prior_logvar && d_grad_mu && d_grad_logvar && d_grad_prior_mu &&
+                      d_grad_prior_logvar && n > 0, MLVAE_ERR_INVALID_ARG, "gmm_reparam_kl_bwd: missing buffers");
+    const bool al = aligned16(d_mu) && aligned16(d_logvar) && aligned16(d_prior_mu) && aligned16(d_prior_logvar) &&
+                    aligned16(d_eps) && aligned16(d_grad_z) && aligned16(d_grad_kl_elem) && aligned16(d_grad_mu) &&
+                    aligned16(d_grad_logvar) && aligned16(d_grad_prior_mu) && aligned16(d_grad_prior_logvar);
+    MLVAE_DISPATCH(dtype, n, al, {
+        gmm_reparam_kl_bwd_kernel<T, VEC><<<grid_for(n / VEC), kThreads, 0, (cudaStream_t)stream>>>(
+            (const T *)d_mu, (const T *)d_logvar, (const T *)d_prior_mu, (const T *)d_prior_logvar, (const T *)d_eps, seed, offset,
+            d_offset_add, (const T *)d_grad_z, (const T *)d_grad_kl_elem, n, (T *)d_grad_mu, (T *)d_grad_logvar,
+            (T *)d_grad_prior_mu, (T *)d_grad_prior_logvar);
+    });
+    MLVAE_CHECK_CUDA(cudaGetLastError());
+    return MLVAE_OK;
+}
+
+int mlvae_apply_weight_fwd(const void *d_x, const void *d_w, int64_t M, int N, int C, int dtype, void *d_out, void *stream) {
+    MLVAE_REQUIRE(d_x && d_w && d_out && M > 0 && N > 0 && C > 0, MLVAE_ERR_INVALID_ARG, "apply_weight_fwd: bad arguments");
+    const int grid = grid_for(M * 32);
+    if (dtype == MLVAE_F32) apply_weight_fwd_kernel<float><<<grid, kThreads, 0, (cudaStream_t)stream>>>((const float *)d_x, (const float *)d_w, M, N, C, (float *)d_out);
+    else if (dtype == MLVAE_BF16) apply_weight_fwd_kernel<__nv_bfloat16><<<grid, kThreads, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)d_x, (const __nv_bfloat16 *)d_w, M, N, C, (__nv_bfloat16 *)d_out);
+    else return fail(MLVAE_ERR_INVALID_ARG, "unknown dtype %d", dtype);
+    MLVAE_CHECK_CUDA(cudaGetLastError());
+    return MLVAE_OK;
+}
+
+int mlvae_apply_weight_bwd(const void *d_x, const void *d_w, const void *d_grad_out, int64_t M, int N, int C, int dtype,
+                           void *d_grad_x, void *d_grad_w, void *stream) {
+    MLVAE_REQUIRE(d_x && d_w && d_grad_out && M > 0 && N > 0 && C > 0, MLVAE_ERR_INVALID_ARG, "apply_weight_bwd: bad arguments");
+    const int grid = grid_for(M * 32);
+    if (dtype == MLVAE_F32) apply_weight_bwd_kernel<float><<<grid, kThreads, 0, (cudaStream_t)stream>>>((const float *)d_x, (const float *)d_w, (const float *)d_grad_out, M, N, C, (float *)d_grad_x, (float *)d_grad_w);
+    else if (dtype == MLVAE_BF16) apply_weight_bwd_kernel<__nv_bfloat16><<<grid, kThreads, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)d_x, (const __nv_bfloat16 *)d_w, (const __nv_bfloat16 *)d_grad_out, M, N, C, (__nv_bfloat16 *)d_grad_x, (__nv_bfloat16 *)d_grad_w);
+    else return fail(MLVAE_ERR_INVALID_ARG, "unknown dtype %d", dtype);
     MLVAE_CHECK_CUDA(cudaGetLastError());
     return MLVAE_OK;
 }

@@ -97,6 +97,85 @@ def reparam_kl(mu, logvar, lens=None, eps=None, seed: int = 0, offset: int = 0,
     return z, (e if want_elem else None), (m if want_mean else None)
 
 
+class _GmmReparamKL(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mu, logvar, pmu, plogvar, eps, seed, offset):
+        L.require_cuda(mu, logvar, pmu, plogvar, eps)
+        mu, logvar, pmu, plogvar, eps = _c(mu), _c(logvar), _c(pmu), _c(plogvar), _c(eps)
+        if not (mu.shape == logvar.shape == pmu.shape == plogvar.shape):
+            raise ValueError("mean, log_var, prior_mean, prior_log_var must have the same shape")
+        if eps is not None:
+            eps = eps.to(mu.dtype).reshape(mu.shape).contiguous()
+        z, kl = torch.empty_like(mu), torch.empty_like(mu)
+        L.check(L.lib().mlvae_gmm_reparam_kl_fwd(L.ptr(mu), L.ptr(logvar), L.ptr(pmu), L.ptr(plogvar), L.ptr(eps), seed, offset,
+                                                 None, mu.numel(), L.dtype_code(mu), L.ptr(z), L.ptr(kl), L.stream_ptr()),
+                "mlvae_gmm_reparam_kl_fwd")
+        ctx.save_for_backward(mu, logvar, pmu, plogvar, eps)
+        ctx.seed, ctx.offset = seed, offset
+        ctx.set_materialize_grads(False)
+        return z, kl
+
+    @staticmethod
+    def backward(ctx, gz, gk):
+        mu, logvar, pmu, plogvar, eps = ctx.saved_tensors
+        gz = _c(gz.to(mu.dtype)) if gz is not None else None
+        gk = _c(gk.to(mu.dtype)) if gk is not None else None
+        outs = [torch.empty_like(mu) for _ in range(4)]
+        L.check(L.lib().mlvae_gmm_reparam_kl_bwd(L.ptr(mu), L.ptr(logvar), L.ptr(pmu), L.ptr(plogvar), L.ptr(eps), ctx.seed,
+                                                 ctx.offset, None, L.ptr(gz), L.ptr(gk), mu.numel(), L.dtype_code(mu),
+                                                 *[L.ptr(o) for o in outs], L.stream_ptr()), "mlvae_gmm_reparam_kl_bwd")
+        return outs[0], outs[1], outs[2], outs[3], None, None, None
+
+
+def gmm_reparam_kl(mu, logvar, prior_mu, prior_logvar, eps=None, seed: int = 0, offset: int = 0):
+    """GMMVAE.reparameterize + compute_kld_loss (modules/gmm_vae.py:51-67) -> (z, unreduced kl)."""
+    return _GmmReparamKL.apply(mu, logvar, prior_mu, prior_logvar, eps, int(seed), int(offset))
+
+
+class _ApplyWeight(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w):
+        L.require_cuda(x, w)
+        B, T, N = w.shape
+        C = x.shape[-1] // N if x.dim() == 3 else x.shape[-1]
+        x = x.reshape(B * T, N, C).contiguous()
+        w = w.reshape(B * T, N).to(x.dtype).contiguous()
+        out = torch.empty(B * T, C, dtype=x.dtype, device=x.device)
+        L.check(L.lib().mlvae_apply_weight_fwd(L.ptr(x), L.ptr(w), B * T, N, C, L.dtype_code(x), L.ptr(out), L.stream_ptr()),
+                "mlvae_apply_weight_fwd")
+        ctx.save_for_backward(x, w)
+        ctx.meta = (B, T, N, C)
+        return out.view(B, T, C)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        B, T, N, C = ctx.meta
+        g = g.reshape(B * T, C).to(x.dtype).contiguous()
+        gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        gw = torch.empty_like(w) if ctx.needs_input_grad[1] else None
+        L.check(L.lib().mlvae_apply_weight_bwd(L.ptr(x), L.ptr(w), L.ptr(g), B * T, N, C, L.dtype_code(x), L.ptr(gx), L.ptr(gw),
+                                               L.stream_ptr()), "mlvae_apply_weight_bwd")
+        return (gx.view(ctx.x_shape) if gx is not None else None), (gw.view(B, T, N) if gw is not None else None)
+
+
+def apply_weight(x, weight):
+    """utils/data_utils.py:32-64: x (B,T,N,C) or (B,T,N*C), weight (B,T,N) -> (B,T,C)."""
+    return _ApplyWeightShaped.apply(x, weight, tuple(x.shape))
+
+
+class _ApplyWeightShaped(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, shape):
+        ctx.x_shape = shape
+        return _ApplyWeight.forward(ctx, x, w)
+
+    @staticmethod
+    def backward(ctx, g):
+        gx, gw = _ApplyWeight.backward(ctx, g)
+        return gx, gw, None
+
+
 class _ReconLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, mean, logvar, target, lens, loss_type, want_elem, want_mean):

@@ -16,3 +16,8 @@ def apply_lens_to_loss(loss, lens, reduction="mean"):
         # pretending to support an unreduced masked output nobody calls
         raise ValueError(f"Invalid reduction: {reduction}")
     return ops.masked_reduce(loss, lens, reduction)
+
+
+def apply_weight(x, weight):
+    """utils/data_utils.py:32-64: x (B,T,N,C) or (B,T,N*C), weight (B,T,N) -> (B,T,C) on one CUDA kernel."""
+    return ops.apply_weight(x, weight)

@@ -34,7 +34,7 @@ REF_SRC = "/root/reference/src"
 GOLD = os.path.join(ROOT, "tests", "golden")
 sys.path.insert(0, ROOT)
 
-from oracle import fbank_np, fbank_ref, philox_ref, vae_ref  # noqa: E402
+from oracle import fbank_np, fbank_ref, hvae_ref, philox_ref, vae_ref  # noqa: E402
 
 
 def import_reference():
@@ -177,6 +177,65 @@ def fbank_cases():
     np.savez_compressed(os.path.join(GOLD, "fbank_cases.npz"), **out)
 
 
+def hvae_case():
+    """GMM-VAE / hierarchical VAE from the reference's own modules, with the two randn_like draws
+    (vanilla, then gmm: h_vae.py:31,38) and the Gumbel noise of F.gumbel_softmax (gmm_vae.py:31) injected."""
+    import_reference()
+    import torch.nn.functional as F
+    from modules.h_vae import HierarchicalVAE
+    B, T, D, L, N, fc = 3, 11, 24, 8, 3, 16
+    g = torch.Generator().manual_seed(4242)
+    feats = torch.randn(B, T, D, generator=g)
+    pi_idx = torch.randint(0, 2, (B, T), generator=g).float()
+    pi = torch.stack([1 - pi_idx, pi_idx], dim=2)
+    eps_v = torch.randn(B, T, L, generator=g)
+    eps_g = torch.randn(B, T, N * L, generator=g)
+    gumbels = -torch.empty(B, T, N).exponential_(generator=g).log()
+    torch.manual_seed(99)
+    ref = HierarchicalVAE([D, fc, fc], L, N)
+    out = {"feats": feats.numpy(), "pi": pi.numpy(), "eps_v": eps_v.numpy(), "eps_g": eps_g.numpy(), "gumbels": gumbels.numpy(),
+           "meta": np.array([B, T, D, L, N, fc], np.int64)}
+    out.update(np_dict("w.", ref.state_dict()))
+    for tag, dt in (("f32", torch.float32), ("f64", torch.float64)):
+        m = ref.to(dt)
+        m.zero_grad()
+        x = feats.to(dt).clone().requires_grad_(True)
+        queue = [eps_v.to(dt), eps_g.to(dt)]
+        orig_randn, orig_gs = torch.randn_like, F.gumbel_softmax
+        torch.randn_like = lambda t, *a, **k: queue.pop(0).reshape(t.shape)
+        F.gumbel_softmax = lambda logits, tau=1, hard=False, **k: hvae_ref.gumbel_softmax_st(logits, gumbels.to(logits.dtype), tau)
+        try:
+            o = m(x, pi.to(dt))
+        finally:
+            torch.randn_like, F.gumbel_softmax = orig_randn, orig_gs
+        cot = [torch.randn(B, T, L, generator=torch.Generator().manual_seed(7 + i)).to(dt) for i in range(4)]
+        scalar = (o["mean"] * cot[0]).sum() + (o["log_var"] * cot[1]).sum() + (o["sampled_h"] * cot[2]).sum() \
+            + (o["losses"]["vae_kld_loss"] * cot[3]).sum()
+        scalar.backward()
+        res = {"mean": o["mean"], "log_var": o["log_var"], "sampled_h": o["sampled_h"], "kld": o["losses"]["vae_kld_loss"],
+               "gmm_weight": o["gmm_weight"], "grad_feats": x.grad}
+        out.update(np_dict(f"{tag}.", res))
+        out.update({f"{tag}.grad.{k}": p.grad.numpy().copy() for k, p in m.named_parameters()})
+        if tag == "f32":
+            out.update({f"cot{i}": c.float().numpy() for i, c in enumerate(cot)})
+        # pin the restatement
+        ps = {k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+        x2 = feats.to(dt).clone().requires_grad_(True)
+        o2 = hvae_ref.hvae_forward(ps, x2, pi.to(dt), eps_v.to(dt), eps_g.to(dt), gumbels.to(dt))
+        s2 = (o2["mean"] * cot[0]).sum() + (o2["log_var"] * cot[1]).sum() + (o2["sampled_h"] * cot[2]).sum() \
+            + (o2["losses"]["vae_kld_loss"] * cot[3]).sum()
+        s2.backward()
+        tol = 2e-6 if dt == torch.float32 else 1e-12
+        chk = [(o2["sampled_h"], o["sampled_h"]), (o2["losses"]["vae_kld_loss"], o["losses"]["vae_kld_loss"]), (x2.grad, x.grad)]
+        chk += [(ps[k].grad, p.grad) for k, p in m.named_parameters()]
+        for a, b in chk:
+            err = (a - b).abs().max().item() / max(b.abs().max().item(), 1e-30)
+            assert err <= tol, ("hvae", tag, err)
+    ref.float()
+    np.savez_compressed(os.path.join(GOLD, "hvae_small.npz"), **out)
+    print("hvae_small written; oracle==reference OK")
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(1)           # deterministic summation order for the stored float32 values
@@ -189,6 +248,7 @@ def main():
              lens=[1.0, 0.9, 0.5, 0.1], seed=20240, hp=hp)
     mask_cases()
     fbank_cases()
+    hvae_case()
 
 
 if __name__ == "__main__":

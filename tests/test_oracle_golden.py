@@ -126,3 +126,28 @@ def test_philox_normal_moments():
     assert abs(e.mean()) < 0.01 and abs(e.std() - 1) < 0.01
     assert abs((e ** 3).mean()) < 0.03 and abs((e ** 4).mean() - 3) < 0.1
     assert not np.array_equal(e[:16], philox_ref.philox_normal(123456, 1, 16))
+
+
+@pytest.mark.parametrize("tag,dtype,tol", [("f32", torch.float32, 5e-6), ("f64", torch.float64, 1e-12)])
+def test_hvae_oracle_matches_reference_golden(tag, dtype, tol):
+    """oracle/hvae_ref.py against the reference's own HierarchicalVAE, forward and gradients."""
+    from oracle import hvae_ref
+    z = _load("hvae_small.npz")
+    params = {k[2:]: torch.from_numpy(z[k]).to(dtype).requires_grad_(True) for k in z.files if k.startswith("w.")}
+    t = lambda k: torch.from_numpy(z[k]).to(dtype)
+    feats = t("feats").requires_grad_(True)
+    o = hvae_ref.hvae_forward(params, feats, t("pi"), t("eps_v"), t("eps_g"), t("gumbels"))
+    s = (o["mean"] * t("cot0")).sum() + (o["log_var"] * t("cot1")).sum() + (o["sampled_h"] * t("cot2")).sum() \
+        + (o["losses"]["vae_kld_loss"] * t("cot3")).sum()
+    s.backward()
+
+    def close(a, key):
+        b = z[f"{tag}.{key}"]
+        a = a.detach().numpy()
+        assert np.abs(a - b).max() <= tol * max(np.abs(b).max(), 1e-30), key
+
+    close(o["mean"], "mean"); close(o["log_var"], "log_var"); close(o["sampled_h"], "sampled_h")
+    close(o["losses"]["vae_kld_loss"], "kld"); close(o["gmm_weight"], "gmm_weight")
+    close(feats.grad, "grad_feats")
+    for k, p in params.items():
+        close(p.grad, f"grad.{k}")
