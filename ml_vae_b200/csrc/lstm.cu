@@ -11,11 +11,18 @@
 // form is bounded by 128*NB/256 cycles per K=16 instruction).  The input projection
 // P = x W_ih^T + b_ih + b_hh for all timesteps is one big GEMM done before the launch.
 //
-// Exchange of h_t inside a group uses a flag-in-data protocol over L2 (no fence / atomic / poll
-// round trips): every producer stores 8-byte words {2 x bf16 h, step tag}; 8-byte stores are
-// single transactions, so a consumer that reads tag == step has the data.  Consumers poll their
-// NB x H/2 words with volatile loads, write the bf16 pairs into the K-major B-operand tile, and
-// one elected thread issues the H/16 tcgen05.mma instructions.  Deterministic; no data atomics.
+// Exchange of h_t inside a group uses a flag-in-data protocol over L2 (no fence / atomic / separate
+// flag round trip).  The step time is set by this exchange and it scales with the bytes every CTA
+// pulls per step (tests/probes/exchange_probe.cu: 960 / 1330 / 2040 cycles for 8 / 16 / 32 KB), so
+// the words carry NO separate tag: |h| <= 1 leaves bit 14 (the exponent MSB) of every bf16 free, and
+// that bit of ALL eight elements of a 16-byte word holds the step tag ((step + 1) >> 1) & 1 -- it
+// alternates between successive uses of a slot and differs from the zeroed initial state.  Every
+// element is validated on its own, so the protocol does not even depend on 16-byte store atomicity.
+// A NaN h (the only value with bit 14 set) travels as 0; the output Y keeps the NaN, so the loss is
+// non-finite exactly when the reference's is.  Consumers write the words into the K-major B-operand
+// tile and elected threads issue the tcgen05.mma instructions.  The backward pass ships its partial
+// dh sums (unbounded, so no free bit) as 8-byte {2 x bf16, step tag} words; a 16-byte bit-tagged
+// variant (values scaled by 2^-64) was measured 8 % slower there.  Deterministic; no data atomics.
 // All CTAs wait on each other, so the launch is cooperative (co-residency guaranteed or refused).
 #include <cooperative_groups.h>
 
@@ -31,8 +38,18 @@ constexpr int kRows = 4 * kUnits;     // gate rows per CTA == MMA M
 constexpr int kLstmThreads = 512;
 constexpr int kLstmWarps = kLstmThreads / 32;
 
+#ifndef MLVAE_LSTM_EXACT_ACT
+// one MUFU.TANH per activation (max relative error 2^-11, below the bf16 rounding of h and of the saved gates)
+__device__ __forceinline__ float tanh_f(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float sigmoid_f(float x) { return fmaf(0.5f, tanh_f(0.5f * x), 0.5f); }
+#else
 __device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float tanh_f(float x) { return __fdividef(2.f, 1.f + __expf(-2.f * x)) - 1.f; }
+#endif
 
 __device__ __forceinline__ uint2 ld_volatile_u2(const uint2 *p) {
     uint2 v;
@@ -41,6 +58,19 @@ __device__ __forceinline__ uint2 ld_volatile_u2(const uint2 *p) {
 }
 __device__ __forceinline__ void st_volatile_u2(uint2 *p, uint2 v) {
     asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ uint4 ld_volatile_u4(const uint4 *p) {
+    uint4 v;
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_volatile_u4(uint4 *p, uint4 v) {
+    asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+constexpr uint32_t kTagBits = 0x40004000u;                       // bit 14 of both bf16 halves
+__device__ __forceinline__ uint32_t step_tag(int step) { return (((step + 1) >> 1) & 1) ? kTagBits : 0u; }
+__device__ __forceinline__ bool tag_ok(const uint4 &w, uint32_t tag) {
+    return (((w.x & kTagBits) == tag) & ((w.y & kTagBits) == tag)) & (((w.z & kTagBits) == tag) & ((w.w & kTagBits) == tag));
 }
 
 __device__ long long *g_prof = nullptr;     // optional per-phase cycle counters (debug / profiles/)
@@ -55,7 +85,7 @@ struct LstmFwdParams {
     const bf16 *Whh;         // (2, 4H, H)
     bf16 *Y;                 // (B, T, 2H)
     float *C;                // (B, T, 2H) cell states (saved for backward) or nullptr
-    uint2 *ll;               // [2 parity][2 * slices groups][NB][H/2] zeroed {data, tag} words
+    uint4 *ll;               // [2 parity][2 * slices groups][G producers][NB rows][4] zeroed words of 8 tagged bf16
     int B, T, H, save;
 };
 
@@ -120,8 +150,8 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_fwd_kernel(LstmFwdParams
     const uint32_t sbo = (uint32_t)(H >> 3) * 128;
     const int groups = 2 * gridDim.y;
     const int group = d * gridDim.y + slice;
-    const size_t ll_words = (size_t)NB * (H / 2);
-    const int n_words = NB * (H / 2);
+    const int G = H / kUnits;                                                 // CTAs (producers) per group
+    const size_t ll_words = (size_t)G * NB * 4;                               // 16-byte words per group and parity
 
     // ---- per-thread constant addressing, hoisted out of the time loop ----
     const int t_first = d ? (T - 1) : 0;
@@ -136,16 +166,16 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_fwd_kernel(LstmFwdParams
     // row) after the transpose reads its pre-activations and writes its activated gates with ONE 8-byte access
     uint2 *pG = reinterpret_cast<uint2 *>(p.P) +
                 (((size_t)min(b0 + my_row, B - 1) * T + t_first) * 2 + d) * (size_t)H + u * kUnits + unit_local;
-    const size_t ll_mine = (size_t)my_row * (H / 2) + (u * kUnits + unit_local) / 2;
-    constexpr int WB = 8;                                                    // exchange words per thread per round
-    // word i = n * 512 + tid -> (batch row j, unit pair kw); its K-major byte offset is computed once (H <= 512
-    // guarantees NB * H/2 <= 512 * WB words)
+    // this warp's eight units of batch row my_row are one exchange word: producer u, row my_row, quarter q, element lane >> 2
+    const size_t ll_mine = ((size_t)u * NB + my_row) * 4 + q;
+    const bool publisher = (lane >> 2) == 0;
+    // consumer side: warp w pulls the NB x 4 words of producer w (1 KB, contiguous): word n * 32 + lane -> row, quarter
+    constexpr int WB = NB * 4 / 32;
     uint32_t soff[WB];
 #pragma unroll
     for (int n = 0; n < WB; ++n) {
-        const int i = n * kLstmThreads + tid;
-        const int j = i / (H / 2), kw = i - j * (H / 2);
-        soff[n] = tc::kmajor_off(j < NB ? j : 0, 2 * kw, H);
+        const int i = n * 32 + lane;
+        soff[n] = tc::kmajor_off(i >> 2, 8 * (4 * (warp < G ? warp : 0) + (i & 3)), H);
     }
     float c_state = 0.f;
 
@@ -160,24 +190,23 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_fwd_kernel(LstmFwdParams
         float acc[CPW];
         if (step > 0) {
             // ---- gather h_{t_prev}: the {data, tag} words of this group, tag == step ----
-            const uint2 *src = p.ll + ((size_t)(step & 1) * groups + group) * ll_words;
-            {
-                const uint2 *wsrc = src + tid;
-                uint2 w[WB];
-                // spin on ONE word per thread (polling all of them floods L2 and delays the producers' stores:
-                // measured 5.7k vs 3.7k cycles), then fetch the rest and re-check each
-                if (tid < n_words) {
-                    w[0] = ld_volatile_u2(wsrc);
-                    while (w[0].y != (uint32_t)step) w[0] = ld_volatile_u2(wsrc);
-                }
+            // Warp w pulls producer w's words (1 KB, coalesced).  Every thread spins on its FIRST word only and then fetches
+            // the second: polling everything saturates L2 (128 CTAs x 16 KB per ~300-cycle round > the ~6 KB/cycle L2 cap)
+            // and delays the producers' stores (1.00 ms), a few representative pollers per warp cost an extra round trip
+            // whenever the other sectors land later (0.97 ms); this form measured 0.94 ms (8-byte {data, tag} words: 1.04 ms).
+            if (warp < G) {
+                const uint4 *src = p.ll + ((size_t)(step & 1) * groups + group) * ll_words + (size_t)warp * (NB * 4);
+                const uint32_t tag = step_tag(step);
+                uint4 w[WB];
+                w[0] = ld_volatile_u4(src + lane);
+                while (!tag_ok(w[0], tag)) w[0] = ld_volatile_u4(src + lane);
 #pragma unroll
-                for (int n = 1; n < WB; ++n)
-                    if (n * kLstmThreads + tid < n_words) w[n] = ld_volatile_u2(wsrc + n * kLstmThreads);
+                for (int n = 1; n < WB; ++n) w[n] = ld_volatile_u4(src + n * 32 + lane);
 #pragma unroll
                 for (int n = 0; n < WB; ++n) {
-                    if (n * kLstmThreads + tid >= n_words) continue;
-                    while (w[n].y != (uint32_t)step) w[n] = ld_volatile_u2(wsrc + n * kLstmThreads);
-                    *reinterpret_cast<uint32_t *>(sH + soff[n]) = w[n].x;
+                    while (!tag_ok(w[n], tag)) w[n] = ld_volatile_u4(src + n * 32 + lane);
+                    *reinterpret_cast<uint4 *>(sH + soff[n]) =
+                        make_uint4(w[n].x & ~kTagBits, w[n].y & ~kTagBits, w[n].z & ~kTagBits, w[n].w & ~kTagBits);
                 }
             }
             tc::fence_proxy_async();
@@ -244,11 +273,18 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_fwd_kernel(LstmFwdParams
         c_state = c;
         const float h = a[3] * tanh_f(c);
         const bf16 hb = __float2bfloat16_rn(h);
-        const uint32_t mine = (uint32_t)__bfloat16_as_ushort(hb);
-        const uint32_t other = __shfl_down_sync(0xffffffffu, mine, 4);       // same batch row, next unit
-        if (!(lane & 4) && step + 1 < T)
-            st_volatile_u2(p.ll + ((size_t)((step + 1) & 1) * groups + group) * ll_words + ll_mine,
-                           make_uint2(mine | (other << 16), (uint32_t)(step + 1)));
+        {
+            uint32_t mine = (uint32_t)__bfloat16_as_ushort(hb);
+            if (mine & 0x4000u) mine = 0;                                    // NaN (|h| <= 1 otherwise): travels as 0, Y keeps it
+            mine |= step_tag(step + 1) & 0xffffu;
+            // assemble the 8 units of this batch row (lanes lane&3 + 4e) in lane e == 0: e0|e1, e2|e3, e4|e5, e6|e7
+            const uint32_t pair = mine | (__shfl_xor_sync(0xffffffffu, mine, 4) << 16);
+            const uint32_t y2 = __shfl_xor_sync(0xffffffffu, pair, 8);
+            const uint32_t z2 = __shfl_xor_sync(0xffffffffu, pair, 16);
+            const uint32_t w2 = __shfl_xor_sync(0xffffffffu, y2, 16);
+            if (publisher && step + 1 < T)
+                st_volatile_u4(p.ll + ((size_t)((step + 1) & 1) * groups + group) * ll_words + ll_mine, make_uint4(pair, y2, z2, w2));
+        }
         // ---- everything below is off the critical path: it overlaps the L2 flight time of the words just published ----
         if (my_ok) {
             *pY = hb;
@@ -539,7 +575,7 @@ int lstm_plan(int B, int H, LstmPlan &pl) {
     MLVAE_REQUIRE((int64_t)pl.G * pl.slices * 2 <= sms, MLVAE_ERR_UNSUPPORTED,
                   "lstm: batch %d x hidden %d needs %d co-resident CTAs (> %d SMs)", B, H, pl.G * pl.slices * 2, sms);
     pl.smem = (size_t)pl.NB * H * 2;
-    pl.ll_bytes = (size_t)2 * 2 * pl.slices * pl.NB * (H / 2) * sizeof(uint2);
+    pl.ll_bytes = (size_t)2 * 2 * pl.slices * pl.G * pl.NB * 4 * sizeof(uint4);
     return MLVAE_OK;
 }
 }  // namespace
@@ -576,7 +612,7 @@ int mlvae_lstm_fwd(void *d_p, const void *d_whh, void *d_y, float *d_c, int B, i
     if (int rc = lstm_plan(B, H, pl)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     MLVAE_CHECK_CUDA(cudaMemsetAsync(d_scratch, 0, pl.ll_bytes, st));
-    LstmFwdParams prm{(bf16 *)d_p, (const bf16 *)d_whh, (bf16 *)d_y, d_c, (uint2 *)d_scratch, B, T, H, save_gates};
+    LstmFwdParams prm{(bf16 *)d_p, (const bf16 *)d_whh, (bf16 *)d_y, d_c, (uint4 *)d_scratch, B, T, H, save_gates};
     void *args[] = {&prm};
     dim3 grid(pl.G, pl.slices, 2), block(kLstmThreads);
     const void *fn = nullptr;
