@@ -215,6 +215,14 @@ int mlvae_linear_fwd(const void *d_x, const void *d_w, const float *d_bias, void
                      int ldx, int ldy, int leaky, void *stream);
 int mlvae_tc05_selftest(const void *d_a, const void *d_b, float *d_d, int N, int K, int a_in_tmem, void *stream);
 
+/* Backward prologue of one Linear(+LeakyReLU) of modules/fc_block.py:9-16 (what autograd derives from it):
+ *   g = dy * (y > 0 ? 1 : slope)   (d_y / d_g both NULL for a bare Linear),   db[N] = sum over the M rows of g (f32).
+ * bf16 (M x N, row stride ld elements), N % 8 == 0, N <= 2048.  d_scratch: mlvae_dense_bwd_scratch_bytes(N) bytes,
+ * zeroed ONCE by the caller (self-resetting).  Deterministic. */
+size_t mlvae_dense_bwd_scratch_bytes(int N);
+int mlvae_dense_bwd_prep(const void *d_dy, const void *d_y, void *d_g, float *d_db, int64_t M, int N, int64_t ld, float slope,
+                         void *d_scratch, void *stream);
+
 /* ------------------------------------------------------------------------- *
  * Persistent bidirectional LSTM recurrence (modules/decoder.py:14-15,22: nn.LSTM(batch_first,
  * bidirectional); one layer per call).  The input projection x W_ih^T + b_ih + b_hh for all

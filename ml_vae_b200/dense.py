@@ -32,6 +32,25 @@ def _launch(x2, w_bf16, bias_f32, n_out, leaky):
     return y
 
 
+_db_scratch = {}
+
+
+def _bwd_prep(dy: torch.Tensor, y):
+    """g = dy * leaky'(y) (y given) and db = column sums of g, one kernel (csrc/dense_bwd.cu)."""
+    M, N = dy.shape
+    key = (dy.device, torch.cuda.current_stream(dy.device).cuda_stream)
+    need = L.lib().mlvae_dense_bwd_scratch_bytes(N)
+    buf = _db_scratch.get(key)
+    if buf is None or buf.numel() < need:
+        buf = torch.zeros(max(need, L.lib().mlvae_dense_bwd_scratch_bytes(256)), dtype=torch.uint8, device=dy.device)
+        _db_scratch[key] = buf
+    g = torch.empty_like(dy) if y is not None else None
+    db = torch.empty(N, dtype=torch.float32, device=dy.device)
+    L.check(L.lib().mlvae_dense_bwd_prep(L.ptr(dy), L.ptr(y), L.ptr(g), L.ptr(db), M, N, N, LEAKY_SLOPE, L.ptr(buf), L.stream_ptr()),
+            "mlvae_dense_bwd_prep")
+    return (g if y is not None else dy), db
+
+
 class _LinearTC(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x2, w, b, leaky):
@@ -45,9 +64,12 @@ class _LinearTC(torch.autograd.Function):
     def backward(ctx, dy):
         x2, wb, y = ctx.saved_tensors
         g = dy.contiguous()
-        if ctx.leaky:
-            g = g * torch.where(y > 0, 1.0, LEAKY_SLOPE).to(g.dtype)
         N, K = wb.shape
+        db = None
+        if N % 8 == 0 and N <= 2048 and g.dtype == torch.bfloat16:
+            g, db = _bwd_prep(g, y if ctx.leaky else None)
+        elif ctx.leaky:
+            g = g * torch.where(y > 0, 1.0, LEAKY_SLOPE).to(g.dtype)
         dx = None
         if ctx.needs_input_grad[0]:
             if _tc_ok(g, K, N):
@@ -55,7 +77,8 @@ class _LinearTC(torch.autograd.Function):
             else:
                 dx = g @ wb
         dw = (g.t() @ x2).float()
-        db = g.sum(0, dtype=torch.float32)
+        if db is None:
+            db = g.sum(0, dtype=torch.float32)
         return dx, dw, db, None
 
 

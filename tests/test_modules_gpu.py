@@ -80,3 +80,20 @@ def test_modules_bf16_within_tolerance(cuda):
     assert_close(eo["kld_loss"], torch.from_numpy(np.asarray(z["f64.kld_loss"])), 3e-2, "bf16 kld")
     g = torch.from_numpy(z["f64.grad.dec.mean_fc.blocks.4.weight"])
     assert_close(dec.mean_fc.blocks._modules["4"].weight.grad, g, 5e-2, "bf16 grad")
+
+
+@pytest.mark.parametrize("M,N", [(1, 8), (37, 80), (1000, 64), (32000, 128), (513, 1024)])
+@pytest.mark.parametrize("leaky", [False, True])
+def test_dense_bwd_prep_kernel(cuda, M, N, leaky):
+    """g = dy * leaky'(y), db = column sums: the fused backward prologue of Linear(+LeakyReLU) (fc_block.py:9-16)."""
+    from ml_vae_b200 import dense
+    g0 = torch.Generator().manual_seed(M + N)
+    dy = torch.randn(M, N, generator=g0).bfloat16().to(cuda)
+    y = torch.randn(M, N, generator=g0).bfloat16().to(cuda)
+    y[0, 0] = 0.0                                                  # LeakyReLU'(0) = slope (torch: y > 0 ? 1 : slope)
+    g, db = dense._bwd_prep(dy, y if leaky else None)
+    want_g = dy.float() * torch.where(y > 0, 1.0, 0.01).float() if leaky else dy.float()
+    assert_close(g.float(), want_g, BF16_RTOL, "g")
+    assert_close(db, g.double().sum(0), 1e-5, "db")               # exact column sums of the rounded g, fp32 accumulation
+    g2, db2 = dense._bwd_prep(dy, y if leaky else None)           # self-resetting scratch, deterministic
+    assert torch.equal(db, db2) and torch.equal(g, g2)
