@@ -202,6 +202,16 @@ int mlvae_global_norm(const float *d_x, const float *d_lens, int B, int T, int D
                       float *d_state, float *d_scratch, void *d_out, int out_dtype, void *stream);
 
 /* ------------------------------------------------------------------------- *
+ * Ragged PCM batch -> padded float32 matrix (replaces the host-side decode + pad of
+ * src/utils/data_io.py:189-196 and the pickled feature cache of data_io.py:67-97 on the training path).
+ * d_blob: the batch's utterances back to back, each start aligned to 8 samples (16 bytes for int16);
+ * sample_dtype 0 = int16, 1 = float32; d_offsets[B] (in samples), d_lens[B];
+ * out (B, n_max) float32 = sample * scale (1/32768 for int16: the libsndfile / librosa convention), zeros past d_lens[b].
+ * ------------------------------------------------------------------------- */
+int mlvae_pcm_unpack(const void *d_blob, int sample_dtype, const int64_t *d_offsets, const int *d_lens, int B,
+                     int64_t n_max, float scale, float *d_out, void *stream);
+
+/* ------------------------------------------------------------------------- *
  * tcgen05 / TMEM dense projections (modules/fc_block.py:4-21 and the mean/log_var
  * heads of vanilla_vae.py:22-24 and decoder.py:24-25).
  * ------------------------------------------------------------------------- */
