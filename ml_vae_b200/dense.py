@@ -76,7 +76,7 @@ class _LinearTC(torch.autograd.Function):
                 dx = _launch(g, wb.t().contiguous(), None, K, False)      # dx = g W  ==  linear(g, W^T)
             else:
                 dx = g @ wb
-        dw = (g.t() @ x2).float()
+        dw = torch.mm(g.t(), x2, out_dtype=torch.float32)       # float32 straight out of the GEMM
         if db is None:
             db = g.sum(0, dtype=torch.float32)
         return dx, dw, db, None

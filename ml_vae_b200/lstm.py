@@ -64,18 +64,28 @@ def _probe_end(tag, start):
         PROBE.append((tag, start, e))
 
 
+def _mm_f32(a, b):
+    """a @ b with bf16 operands and a float32 result straight out of the GEMM (no bf16 rounding + cast kernel)."""
+    return torch.mm(a, b, out_dtype=torch.float32)
+
+
 class _BiLSTMLayer(torch.autograd.Function):
+    """One bidirectional layer.  Takes torch's eight per-direction float32 master parameters directly and hands their
+    gradients back in float32, so autograd needs no cat / cast / add nodes (and their kernels) around the layer."""
+
     @staticmethod
-    def forward(ctx, x, w_ih, w_hh, bias, training):
-        """x (B,T,In) bf16; w_ih (8H,In) bf16 [fwd rows then reverse rows]; w_hh (2,4H,H) bf16;
-        bias (8H,) bf16 = b_ih + b_hh of both directions -> y (B,T,2H) bf16."""
+    def forward(ctx, x, w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r, training):
+        """x (B,T,In) bf16 -> y (B,T,2H) bf16."""
         B, T, In = x.shape
-        H = w_hh.shape[2]
+        H = w_hh_f.shape[1]
+        bf = torch.bfloat16
         x2 = x.reshape(B * T, In)
         perm, _ = _gate_perm(H, x.device)
-        w_ih_p = w_ih[perm]                                                   # rows in (dir, unit, gate) order
-        P = torch.addmm(bias[perm], x2, w_ih_p.t()).view(B, T, 2, 4 * H)     # library GEMM (time-parallel)
-        y = torch.empty(B, T, 2 * H, dtype=torch.bfloat16, device=x.device)
+        w_ih_p = torch.cat([w_ih_f, w_ih_r], 0).to(bf)[perm]                 # (8H, In), rows in (dir, unit, gate) order
+        w_hh = torch.stack([w_hh_f, w_hh_r], 0).to(bf)                       # (2, 4H, H)
+        bias_p = torch.cat([b_ih_f + b_hh_f, b_ih_r + b_hh_r], 0).to(bf)[perm]
+        P = torch.addmm(bias_p, x2, w_ih_p.t()).view(B, T, 2, 4 * H)         # library GEMM (time-parallel)
+        y = torch.empty(B, T, 2 * H, dtype=bf, device=x.device)
         c = torch.empty(B, T, 2 * H, dtype=torch.float32, device=x.device) if training else None
         ev = _probe_start()
         L.check(L.lib().mlvae_lstm_fwd(L.ptr(P), L.ptr(w_hh), L.ptr(y), L.ptr(c), B, T, H, int(training),
@@ -100,31 +110,27 @@ class _BiLSTMLayer(torch.autograd.Function):
         dA2 = dA.view(B * T, 8 * H)                                        # columns in (dir, unit, gate) order
         _, inv = _gate_perm(H, x.device)
         x2 = x.reshape(B * T, In)
-        dx = (dA2 @ w_ih_p).view(B, T, In)
-        dw_ih = (dA2.t() @ x2)[inv]
-        db = db_part.sum(0)                                                # bias gradient, reduced inside the kernel
-        dw_hh = torch.empty_like(w_hh)
+        dx = (dA2 @ w_ih_p).view(B, T, In) if ctx.needs_input_grad[0] else None
+        dw_ih = _mm_f32(dA2.t(), x2)[inv]                                  # (8H, In) float32, torch row order
+        db = db_part.sum(0)                                                # bias gradient, reduced inside the kernel (torch order)
+        H4 = 4 * H
         if T > 1:
             # dW_hh[d] = sum_{b,t} dA[b,t,d]^T h_prev[b,t,d] with h_prev the previous step IN THAT DIRECTION'S ORDER
             # (forward: y[b,t-1,:H]; reverse: y[b,t+1,H:]).  On the flattened (B*T) row axis that is one strided GEMM
             # of rows r against rows r-1 (r+1) -- no copies -- minus the B-1 pairs that straddle two utterances.
             y2 = y.view(B * T, 2 * H)
-            g0 = dA2[1:, :4 * H].t() @ y2[:-1, :H]
-            g1 = dA2[:-1, 4 * H:].t() @ y2[1:, H:]
+            g0 = _mm_f32(dA2[1:, :H4].t(), y2[:-1, :H])
+            g1 = _mm_f32(dA2[:-1, H4:].t(), y2[1:, H:])
             if B > 1:
-                g0 -= dA[1:, 0, 0].t() @ y[:-1, T - 1, :H]
-                g1 -= dA[:-1, T - 1, 1].t() @ y[1:, 0, H:]
-            dw_hh[0] = g0[inv[:4 * H]]
-            dw_hh[1] = g1[inv[:4 * H]]
+                g0 -= _mm_f32(dA[1:, 0, 0].t(), y[:-1, T - 1, :H])
+                g1 -= _mm_f32(dA[:-1, T - 1, 1].t(), y[1:, 0, H:])
+            dw_hh_f, dw_hh_r = g0[inv[:H4]], g1[inv[:H4]]
         else:
-            dw_hh.zero_()
-        return dx, dw_ih, dw_hh, db.to(torch.bfloat16), None
+            dw_hh_f = torch.zeros(H4, H, dtype=torch.float32, device=x.device)
+            dw_hh_r = torch.zeros_like(dw_hh_f)
+        return dx, dw_ih[:H4], dw_hh_f, db[:H4], db[:H4], dw_ih[H4:], dw_hh_r, db[H4:], db[H4:], None
 
 
 def bilstm_layer(x, w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r, training: bool):
-    """One bidirectional layer with torch's per-direction parameters (float32 masters are cast here)."""
-    bf = torch.bfloat16
-    w_ih = torch.cat([w_ih_f, w_ih_r], 0).to(bf)
-    w_hh = torch.stack([w_hh_f, w_hh_r], 0).to(bf)
-    bias = torch.cat([b_ih_f + b_hh_f, b_ih_r + b_hh_r], 0).to(bf)
-    return _BiLSTMLayer.apply(x.contiguous(), w_ih, w_hh, bias, training)
+    """One bidirectional layer with torch's per-direction parameters (float32 masters; cast inside the layer)."""
+    return _BiLSTMLayer.apply(x.contiguous(), w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r, training)
