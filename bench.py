@@ -158,7 +158,7 @@ def run_reference(args):
                              "sample": f"{batch} x 5 s utterances per step (bounded sample of the 64-utterance batch), "
                                        "oracle port of the reference's torch CPU path incl. restated SpeechBrain Fbank"},
             "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(n_gpus, batch_per_gpu):
@@ -204,7 +204,7 @@ def run_ours(args):
     enc = VanillaVAE([D, W["enc_fc"], W["enc_fc"]], W["latent"]).to(dev)
     dec = Decoder(W["latent"], W["rnn_hidden"], W["rnn_layers"], 0.0, [2 * W["rnn_hidden"], W["dec_fc"], W["dec_fc"], D]).to(dev)
     ts = TrainStep(fb, InputNormalization().to(dev), enc, dec, {"kld_weight": 0.001, "batch_size": B}, lr=1e-3,
-                   compute_dtype=dtype, world_size=world)
+                   compute_dtype=dtype, world_size=world, overlap_all_reduce=args.overlap)
 
     g = torch.Generator().manual_seed(123456 + rank)
     R = 4                                                       # distinct resident batches, rotated
@@ -368,7 +368,7 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": round(v, 3), "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": "8 x 5 s utterances per step, 1 warm-up + 2 timed fwd+bwd+Adam steps of "
                                               "the oracle port (restated SpeechBrain Fbank + reference VAE modules), fp32"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         # release the captured graph (it references the communicator) before tearing the process group down, and do
         # not let a teardown hang outlive the measurement: everything has been printed by now
@@ -378,6 +378,26 @@ def run_ours(args):
         sys.stdout.flush()
         sys.stderr.flush()
         os._exit(0)
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """stdout carries exactly ONE line, the JSON result: everything libraries write to fd 1 meanwhile (NCCL prints its
+    version banner there) is sent to stderr."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+    else:
+        print(json.dumps(line), flush=True)
 
 
 def main():
@@ -391,7 +411,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", default="", help="write a torch.profiler kernel table of 3 steps to this path")
     ap.add_argument("--no-graph", action="store_true", help="do not capture the step in a CUDA graph")
+    ap.add_argument("--overlap", action="store_true", help="all-reduce the tail of the gradient bucket under the first LSTM layer's backward (measured slower at N=2)")
     args = ap.parse_args()
+    quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

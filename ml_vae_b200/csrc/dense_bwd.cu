@@ -134,8 +134,9 @@ int mlvae_dense_bwd_prep(const void *d_dy, const void *d_y, void *d_g, float *d_
                   "dense_bwd_prep: needs N %% 8 == 0, N <= 2048 and 16-byte aligned rows (N=%d, ld=%lld)", N, (long long)ld);
     const int VC = N / 8, RP = kDbThreads / VC;
     MLVAE_REQUIRE(RP >= 1, MLVAE_ERR_UNSUPPORTED, "dense_bwd_prep: N too large");
-    int64_t blocks = (M + RP - 1) / RP;
-    const int grid = (int)(blocks < kDbMaxGrid ? blocks : kDbMaxGrid);
+    // enough CTAs to keep ~kDbUnroll rows in flight per thread, no more: every extra CTA is another partial for the last one to sum
+    int64_t blocks = (M + (int64_t)RP * kDbUnroll - 1) / ((int64_t)RP * kDbUnroll);
+    const int grid = (int)(blocks < 1 ? 1 : blocks < kDbMaxGrid ? blocks : kDbMaxGrid);
     const size_t smem = (size_t)RP * N * sizeof(float);
     dense_bwd_prep_kernel<<<grid, kDbThreads, smem, (cudaStream_t)stream>>>((const bf16 *)d_dy, (const bf16 *)d_y, (bf16 *)d_g, d_db, M,
                                                                              N, ld, slope, (DbScratch *)d_scratch);

@@ -7,8 +7,8 @@ mean_fc.blocks.{0,2,4}.*, log_var_fc.blocks.{0,2,4}.*) and forward() dict
 loss_type raises ValueError exactly like decoder.py:51.
 
 The reconstruction loss (and, with ``lens=``, its length-masked mean) is one fused
-kernel; the dead Normal.log_prob of decoder.py:45-47 is not computed.  The biLSTM is
-cuDNN through torch (SURVEY.md section 8f-1 ranks its replacement first among the "next" rows).
+kernel; the dead Normal.log_prob of decoder.py:45-47 is not computed.  bf16 activations run the
+biLSTM on the persistent tcgen05 recurrence (lstm.py); float32 stays on cuDNN.
 """
 from __future__ import annotations
 
@@ -32,6 +32,7 @@ class Decoder(nn.Module):
         self.loss_type = loss_type
         self.materialize_loss = materialize_loss
         self.use_persistent_lstm = True
+        self.top_layer_grad_hook = None      # callable(grad): runs in backward once the top LSTM layer's and the heads' gradients exist
         self._rnn_names = []
         for name, p in torch_default_lstm(self.input_size, self.hidden, self.num_layers):
             attach(self, f"rnn.{name}", p)
@@ -56,6 +57,8 @@ class Decoder(nn.Module):
             for layer in range(self.num_layers):
                 ps = [getattr(self.rnn, f"{kind}_l{layer}{sfx}") for sfx in ("", "_reverse")
                       for kind in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")]
+                if layer + 1 == self.num_layers and layer > 0 and self.top_layer_grad_hook is not None and x.requires_grad:
+                    x.register_hook(self.top_layer_grad_hook)       # train_step.py: early all-reduce of the tail of the bucket
                 x = lstm.bilstm_layer(x, *ps, training=need_grad)
                 if self.rnn_dropout > 0 and self.training and layer + 1 < self.num_layers:
                     x = torch.nn.functional.dropout(x, self.rnn_dropout, True)
