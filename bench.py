@@ -341,13 +341,13 @@ def run_ours(args):
                                         "share_of_step": round(sum(vs) / probe_steps / step_ms, 4)}
         roof = {"bound": "tensor", "kernel": "persistent biLSTM recurrence (lstm_fwd_kernel + lstm_bwd_kernel, tcgen05 + TMEM-resident W_hh)",
                 "achieved": round(flops / (per_launch * 1e-3) / 1e12, 1), "peak": tflops_peak, "unit": "TFLOP/s",
-                "frac": round(flops / (per_launch * 1e-3) / 1e12 / tflops_peak, 4), "traffic": 386e6 * T_frames / 300,
+                "frac": round(flops / (per_launch * 1e-3) / 1e12 / tflops_peak, 4), "traffic": 383.2e6 * T_frames / 300,
                 "peak_source": "measured bf16_tflops_sustained (MEASURED_PEAKS.json)", "algorithmic_flops_per_launch": flops,
                 "ms_per_launch": round(per_launch, 4), "share_of_step": round(per_step / step_ms, 4),
-                "note": "latency-bound by construction: T=500 dependent timesteps per launch (2.5 us each: L2 exchange of h_t + "
+                "note": "latency-bound by construction: T=500 dependent timesteps per launch (1.9-2.3 us each: L2 exchange of h_t + "
                         "32 small MMAs + gate math); the roofline fraction is low because the recurrence exposes only "
                         "64x2048x512 MACs of parallelism per step, not because of wasted traffic (ncu: dram bytes = P + gates + "
-                        "cell states + outputs, no re-reads; profiles/r01_lstm_ncu_raw.csv). cuDNN's bf16 path takes 5x longer."}
+                        "cell states + outputs, no re-reads; profiles/r01_lstm_final_ncu_raw.csv: 383 MB per forward launch at T=300, scaled to T=500 here). cuDNN's bf16 path takes 9x longer."}
     else:
         roof = {"bound": "hbm", "kernel": "fused fbank front-end", "achieved": kernels["fbank(memset+logmel+finish)"]["achieved_gbs"],
                 "peak": peak, "unit": "GB/s", "frac": kernels["fbank(memset+logmel+finish)"]["frac_of_hbm_peak"], "traffic": None,
