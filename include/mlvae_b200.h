@@ -264,6 +264,16 @@ int mlvae_lstm_fwd(void *d_p, const void *d_whh, void *d_y, float *d_c, int B, i
 int mlvae_lstm_bwd(void *d_gates, const float *d_c, const void *d_dy, const void *d_whh, float *d_bias_grad_part,
                    int B, int T, int H, void *d_scratch, void *stream);
 
+/* Parameter plumbing of one bidirectional layer (nn.LSTM's parameters, modules/decoder.py:14-15): masters[8] / grads[8] =
+ * {weight_ih, weight_hh, bias_ih, bias_hh} of the forward direction then of the _reverse one, float32 device pointers in
+ * torch's (gate, unit) row order.  pack: -> bf16 W_ih (8H x In) with rows in the kernels' (direction, unit, gate) order,
+ * bf16 W_hh (2, 4H, H), bf16 bias (8H) = b_ih + b_hh in kernel order.  unpack: float32 gradients dW_ih (8H x In) and
+ * dW_hh (4H x H per direction, NULL when T == 1) in kernel row order and db (8H, torch order, both biases) are
+ * un-permuted and ACCUMULATED into grads[].  In % 4 == 0, H % 4 == 0, weights 16-byte aligned. */
+int mlvae_lstm_pack_weights(const float *const *masters, int In, int H, void *d_w_ih_p, void *d_w_hh, void *d_bias_p, void *stream);
+int mlvae_lstm_unpack_grads(const float *d_dw_ih_p, const float *d_dw_hh_p0, const float *d_dw_hh_p1, const float *d_db, int In, int H,
+                            float *const *grads, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -54,6 +54,8 @@ SIGNATURES = {
     "mlvae_linear_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "mlvae_dense_bwd_scratch_bytes": (C.c_size_t, [_i]),
     "mlvae_dense_bwd_prep": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i64, C.c_float, _vp, _vp]),
+    "mlvae_lstm_pack_weights": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "mlvae_lstm_unpack_grads": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "mlvae_pcm_unpack": (_i, [_vp, _i, _vp, _vp, _i, _i64, C.c_float, _vp, _vp]),
     "mlvae_tc05_selftest": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "mlvae_fbank_fwd": (_i, [_vp, _vp, _vp, _i, _i64, _i64, _i, _vp, _i, _i, _vp, _vp, _vp]),

@@ -69,21 +69,41 @@ def _mm_f32(a, b):
     return torch.mm(a, b, out_dtype=torch.float32)
 
 
+def _ptr_array(tensors):
+    import ctypes as C
+    return (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+
+def _packable(masters, In: int, H: int) -> bool:
+    return In % 4 == 0 and H % 4 == 0 and all(m.dtype == torch.float32 and m.is_contiguous() and m.data_ptr() % 16 == 0
+                                              for m in masters)
+
+
 class _BiLSTMLayer(torch.autograd.Function):
     """One bidirectional layer.  Takes torch's eight per-direction float32 master parameters directly and hands their
     gradients back in float32, so autograd needs no cat / cast / add nodes (and their kernels) around the layer."""
 
     @staticmethod
-    def forward(ctx, x, w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r, training):
+    def forward(ctx, x, w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r, training, direct_grads):
         """x (B,T,In) bf16 -> y (B,T,2H) bf16."""
         B, T, In = x.shape
         H = w_hh_f.shape[1]
         bf = torch.bfloat16
         x2 = x.reshape(B * T, In)
-        perm, _ = _gate_perm(H, x.device)
-        w_ih_p = torch.cat([w_ih_f, w_ih_r], 0).to(bf)[perm]                 # (8H, In), rows in (dir, unit, gate) order
-        w_hh = torch.stack([w_hh_f, w_hh_r], 0).to(bf)                       # (2, 4H, H)
-        bias_p = torch.cat([b_ih_f + b_hh_f, b_ih_r + b_hh_r], 0).to(bf)[perm]
+        masters = (w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r)
+        if _packable(masters, In, H):
+            # one launch: cast + stack + permute (csrc/lstm_pack.cu)
+            w_ih_p = torch.empty(8 * H, In, dtype=bf, device=x.device)       # rows in (dir, unit, gate) order
+            w_hh = torch.empty(2, 4 * H, H, dtype=bf, device=x.device)
+            bias_p = torch.empty(8 * H, dtype=bf, device=x.device)
+            L.check(L.lib().mlvae_lstm_pack_weights(_ptr_array(masters), In, H, L.ptr(w_ih_p), L.ptr(w_hh), L.ptr(bias_p),
+                                                    L.stream_ptr()), "mlvae_lstm_pack_weights")
+        else:
+            perm, _ = _gate_perm(H, x.device)
+            w_ih_p = torch.cat([w_ih_f, w_ih_r], 0).to(bf)[perm]
+            w_hh = torch.stack([w_hh_f, w_hh_r], 0).to(bf)
+            bias_p = torch.cat([b_ih_f + b_hh_f, b_ih_r + b_hh_r], 0).to(bf)[perm]
+        ctx.masters = masters if (training and direct_grads) else None
         P = torch.addmm(bias_p, x2, w_ih_p.t()).view(B, T, 2, 4 * H)         # library GEMM (time-parallel)
         y = torch.empty(B, T, 2 * H, dtype=bf, device=x.device)
         c = torch.empty(B, T, 2 * H, dtype=torch.float32, device=x.device) if training else None
@@ -111,9 +131,26 @@ class _BiLSTMLayer(torch.autograd.Function):
         _, inv = _gate_perm(H, x.device)
         x2 = x.reshape(B * T, In)
         dx = (dA2 @ w_ih_p).view(B, T, In) if ctx.needs_input_grad[0] else None
-        dw_ih = _mm_f32(dA2.t(), x2)[inv]                                  # (8H, In) float32, torch row order
+        dw_ih_p = _mm_f32(dA2.t(), x2)                                     # (8H, In) float32, kernel row order
         db = db_part.sum(0)                                                # bias gradient, reduced inside the kernel (torch order)
         H4 = 4 * H
+        masters = ctx.masters
+        if masters is not None and all(m.grad is not None and m.grad.dtype == torch.float32 and m.grad.is_contiguous()
+                                       and m.grad.data_ptr() % 16 == 0 for m in masters) and In % 4 == 0 and H % 4 == 0:
+            # the owner of the parameters keeps float32 gradient buffers (train_step.FlatArena): un-permute and ACCUMULATE
+            # all eight gradients into them in one launch; autograd gets nothing to add
+            g0 = g1 = None
+            if T > 1:
+                y2 = y.view(B * T, 2 * H)
+                g0 = _mm_f32(dA2[1:, :H4].t(), y2[:-1, :H])
+                g1 = _mm_f32(dA2[:-1, H4:].t(), y2[1:, H:])
+                if B > 1:
+                    g0 -= _mm_f32(dA[1:, 0, 0].t(), y[:-1, T - 1, :H])
+                    g1 -= _mm_f32(dA[:-1, T - 1, 1].t(), y[1:, 0, H:])
+            L.check(L.lib().mlvae_lstm_unpack_grads(L.ptr(dw_ih_p), L.ptr(g0), L.ptr(g1), L.ptr(db), In, H,
+                                                    _ptr_array([m.grad for m in masters]), L.stream_ptr()), "mlvae_lstm_unpack_grads")
+            return (dx,) + (None,) * 10
+        dw_ih = dw_ih_p[inv]                                               # torch row order
         if T > 1:
             # dW_hh[d] = sum_{b,t} dA[b,t,d]^T h_prev[b,t,d] with h_prev the previous step IN THAT DIRECTION'S ORDER
             # (forward: y[b,t-1,:H]; reverse: y[b,t+1,H:]).  On the flattened (B*T) row axis that is one strided GEMM
@@ -128,9 +165,12 @@ class _BiLSTMLayer(torch.autograd.Function):
         else:
             dw_hh_f = torch.zeros(H4, H, dtype=torch.float32, device=x.device)
             dw_hh_r = torch.zeros_like(dw_hh_f)
-        return dx, dw_ih[:H4], dw_hh_f, db[:H4], db[:H4], dw_ih[H4:], dw_hh_r, db[H4:], db[H4:], None
+        return dx, dw_ih[:H4], dw_hh_f, db[:H4], db[:H4], dw_ih[H4:], dw_hh_r, db[H4:], db[H4:], None, None
 
 
-def bilstm_layer(x, w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r, training: bool):
-    """One bidirectional layer with torch's per-direction parameters (float32 masters; cast inside the layer)."""
-    return _BiLSTMLayer.apply(x.contiguous(), w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r, training)
+def bilstm_layer(x, w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r, training: bool, direct_grads: bool = False):
+    """One bidirectional layer with torch's per-direction parameters (float32 masters; cast inside the layer).
+    ``direct_grads``: accumulate the parameter gradients straight into the parameters' existing float32 ``.grad``
+    buffers (valid under ``loss.backward()``; the training step that owns a flat gradient bucket turns it on)."""
+    return _BiLSTMLayer.apply(x.contiguous(), w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r, training,
+                              direct_grads)

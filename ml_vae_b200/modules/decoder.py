@@ -32,6 +32,7 @@ class Decoder(nn.Module):
         self.loss_type = loss_type
         self.materialize_loss = materialize_loss
         self.use_persistent_lstm = True
+        self.direct_param_grads = False       # train_step.py: LSTM gradients accumulate straight into the flat bucket
         self.top_layer_grad_hook = None      # callable(grad): runs in backward once the top LSTM layer's and the heads' gradients exist
         self._rnn_names = []
         for name, p in torch_default_lstm(self.input_size, self.hidden, self.num_layers):
@@ -59,7 +60,7 @@ class Decoder(nn.Module):
                       for kind in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")]
                 if layer + 1 == self.num_layers and layer > 0 and self.top_layer_grad_hook is not None and x.requires_grad:
                     x.register_hook(self.top_layer_grad_hook)       # train_step.py: early all-reduce of the tail of the bucket
-                x = lstm.bilstm_layer(x, *ps, training=need_grad)
+                x = lstm.bilstm_layer(x, *ps, training=need_grad, direct_grads=self.direct_param_grads)
                 if self.rnn_dropout > 0 and self.training and layer + 1 < self.num_layers:
                     x = torch.nn.functional.dropout(x, self.rnn_dropout, True)
             return x

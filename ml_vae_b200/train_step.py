@@ -100,6 +100,8 @@ class TrainStep:
         self.encoder.set_seed(seed)
         self.encoder.materialize_loss = False
         self.decoder.materialize_loss = False
+        if hasattr(self.decoder, "direct_param_grads"):
+            self.decoder.direct_param_grads = True         # parameter gradients of the LSTM land in the flat bucket directly
         self.found_inf = torch.zeros((), dtype=torch.float32, device=self.arena.flat.device)
         self.last = {}
         # device-resident step counter = Philox offset of the reparameterisation noise: a captured CUDA graph then

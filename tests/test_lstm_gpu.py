@@ -5,7 +5,7 @@ same bf16-rounded weights and inputs."""
 import pytest
 import torch
 
-from _util import BF16_RTOL, rel_err
+from _util import BF16_RTOL, assert_close, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -109,3 +109,38 @@ def test_tcgen05_linear_fwd_bwd_vs_torch(cuda, M, K, N, leaky):
     assert rel_err(y, yr) < BF16_RTOL
     assert rel_err(hx, gx) < BF16_RTOL
     assert rel_err(hw, gw) < BF16_RTOL and rel_err(hb, gb) < BF16_RTOL
+
+
+def test_pack_and_direct_gradients_match_autograd_path(cuda):
+    """csrc/lstm_pack.cu: one-launch weight packing and the direct accumulation of the eight parameter gradients into
+    existing float32 .grad buffers give the same numbers as the torch cat/cast/gather + AccumulateGrad path."""
+    from ml_vae_b200.lstm import bilstm_layer
+    torch.manual_seed(3)
+    B, T, In, H = 5, 9, 24, 64
+    names = [f"{k}_{d}" for d in ("f", "r") for k in ("w_ih", "w_hh", "b_ih", "b_hh")]
+    shapes = {"w_ih": (4 * H, In), "w_hh": (4 * H, H), "b_ih": (4 * H,), "b_hh": (4 * H,)}
+    base = [0.2 * torch.randn(shapes[n[:-2]], device=cuda) for n in names]
+    x = torch.randn(B, T, In, device=cuda).bfloat16()
+    gy = torch.randn(B, T, 2 * H, device=cuda).bfloat16()
+
+    def run(direct, misalign):
+        ps = []
+        for b in base:
+            if misalign:                                         # 4-byte aligned views: the torch fallback of the packing
+                buf = torch.empty(b.numel() + 1, device=cuda)
+                p = buf[1:].view(b.shape).copy_(b).requires_grad_(True)
+            else:
+                p = b.clone().requires_grad_(True)
+            p.grad = torch.full_like(p, 0.5) if not misalign else None      # pre-existing gradient: must be accumulated into
+            ps.append(p)
+        y = bilstm_layer(x, *ps, training=True, direct_grads=direct)
+        (y.float() * gy.float()).sum().backward()
+        return y, [p.grad - (0.5 if not misalign else 0.0) for p in ps]
+
+    y0, g0 = run(False, False)
+    y1, g1 = run(True, False)
+    y2, g2 = run(False, True)
+    assert torch.equal(y0, y1) and torch.equal(y0, y2)
+    for n, a, b, c in zip(names, g0, g1, g2):
+        assert_close(b, a, 1e-5, f"direct grad {n}")
+        assert_close(c, a, 1e-5, f"fallback grad {n}")
