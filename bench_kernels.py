@@ -134,6 +134,68 @@ def main():
                 B * n * 4 + B * T * D * s, m, mn)
             del wav
 
+    if not args.only or "hvae" in args.only:
+        # GMM-VAE / H-VAE family: KL against a learned prior + reparameterise, mixture selection
+        for dt, sz, name in ((torch.bfloat16, 2, "bf16"), (torch.float32, 4, "f32")):
+            for M, NL in ([(1 << 20, 3 * 64)] if args.quick else [(1 << 20, 3 * 64), (4 << 20, 3 * 64), (1 << 20, 8 * 128)]):
+                ts = [torch.randn(M, NL, device=dev, dtype=dt).clamp_(-3, 3) for _ in range(6)]
+                mu, lv, pmu, plv, gz, gk = ts
+                z, kl = torch.empty_like(mu), torch.empty_like(mu)
+                outs = [torch.empty_like(mu) for _ in range(4)]
+                code, lib, st = L.dtype_code(mu), L.lib(), L.stream_ptr()
+
+                def gfwd():
+                    L.check(lib.mlvae_gmm_reparam_kl_fwd(L.ptr(mu), L.ptr(lv), L.ptr(pmu), L.ptr(plv), None, 1, 0, None, mu.numel(),
+                                                         code, L.ptr(z), L.ptr(kl), st))
+
+                def gbwd():
+                    L.check(lib.mlvae_gmm_reparam_kl_bwd(L.ptr(mu), L.ptr(lv), L.ptr(pmu), L.ptr(plv), None, 1, 0, None, L.ptr(gz),
+                                                         L.ptr(gk), mu.numel(), code, *[L.ptr(o) for o in outs], st))
+                big = M * NL * sz * 6 > (200 << 20)
+                m, mn = time_ms(gfwd, None if big else flush)
+                rec("gmm_reparam_kl_fwd(philox)", (M, NL), name, 6 * M * NL * sz, m, mn)
+                m, mn = time_ms(gbwd, None if big else flush)
+                rec("gmm_reparam_kl_bwd(philox)", (M, NL), name, 10 * M * NL * sz, m, mn)
+                # apply_weight: x (M, N=3, C) -> (M, C)
+                N, C = 3, NL // 3
+                w = torch.rand(M, N, device=dev, dtype=dt)
+                out = torch.empty(M, C, device=dev, dtype=dt)
+                gx, gw = torch.empty_like(mu), torch.empty_like(w)
+                go = gz[:, :C].contiguous()
+
+                def afwd():
+                    L.check(lib.mlvae_apply_weight_fwd(L.ptr(mu), L.ptr(w), M, N, C, code, L.ptr(out), st))
+
+                def abwd():
+                    L.check(lib.mlvae_apply_weight_bwd(L.ptr(mu), L.ptr(w), L.ptr(go), M, N, C, code, L.ptr(gx), L.ptr(gw), st))
+                m, mn = time_ms(afwd, None if big else flush)
+                rec("apply_weight_fwd", (M, N, C), name, (M * N * C + M * N + M * C) * sz, m, mn)
+                m, mn = time_ms(abwd, None if big else flush)
+                rec("apply_weight_bwd", (M, N, C), name, (2 * M * N * C + 2 * M * N + M * C) * sz, m, mn)
+                del ts, mu, lv, pmu, plv, gz, gk, z, kl, outs, w, out, gx, gw, go
+                torch.cuda.empty_cache()
+
+    if not args.only or "dense" in args.only:
+        from ml_vae_b200 import dense
+        for M, N in [(32000, 128), (1 << 20, 64), (1 << 20, 128)]:
+            dy = torch.randn(M, N, device=dev).bfloat16()
+            y = torch.randn(M, N, device=dev).bfloat16()
+            m, mn = time_ms(lambda: dense._bwd_prep(dy, y), flush)
+            rec("dense_bwd_prep(leaky+db)", (M, N), "bf16", 3 * M * N * 2, m, mn)
+            m, mn = time_ms(lambda: dense._bwd_prep(dy, None), flush)
+            rec("dense_bwd_prep(db)", (M, N), "bf16", M * N * 2, m, mn)
+
+    if not args.only or "pcm" in args.only:
+        for B, n in [(64, 80000), (512, 80000)]:
+            blob = torch.randint(-32768, 32767, (B * n,), device=dev, dtype=torch.int16)
+            offs = torch.arange(B, device=dev, dtype=torch.int64) * n
+            lens = torch.full((B,), n, device=dev, dtype=torch.int32)
+            out = torch.empty(B, n, device=dev)
+            f = lambda: L.check(L.lib().mlvae_pcm_unpack(L.ptr(blob), 0, L.ptr(offs), L.ptr(lens), B, n, 1.0 / 32768.0, L.ptr(out),
+                                                         L.stream_ptr()))
+            m, mn = time_ms(f, flush)
+            rec("pcm_unpack(int16->f32)", (B, n), "i16", B * n * 6, m, mn)
+
     if args.out:
         os.makedirs(os.path.dirname(os.path.join(ROOT, args.out)), exist_ok=True)
         json.dump({"peak_gbs": peak, "rows": rows}, open(os.path.join(ROOT, args.out), "w"), indent=1)

@@ -70,3 +70,23 @@ def test_gmm_kernels_vs_oracle(cuda, dtype):
     assert_close(out.float(), hvae_ref.apply_weight(x.double(), w.double()), rtol, "apply_weight")
     assert_close(xd.grad.float(), xr.grad, rtol, "grad x")
     assert_close(wd.grad.float(), wr.grad, rtol if dtype == torch.float32 else 3e-2, "grad w")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,T,N,C", [(5, 37, 3, 64), (2, 9, 4, 256), (3, 11, 2, 20), (1, 1, 5, 7)])
+def test_apply_weight_shapes(cuda, dtype, B, T, N, C):
+    """Vector path (C multiple of the 16-byte vector, power-of-two vectors per row) and the scalar fallback."""
+    from ml_vae_b200 import ops
+    g = torch.Generator().manual_seed(B * 1000 + C)
+    x = torch.randn(B, T, N, C, generator=g).to(dtype)
+    w = torch.rand(B, T, N, generator=g).to(dtype)
+    go = torch.randn(B, T, C, generator=g).to(dtype)
+    xr, wr = x.double().requires_grad_(True), w.double().requires_grad_(True)
+    (hvae_ref.apply_weight(xr, wr) * go.double()).sum().backward()
+    xd, wd = x.to(cuda).requires_grad_(True), w.to(cuda).requires_grad_(True)
+    out = ops.apply_weight(xd, wd)
+    (out.float() * go.to(cuda).float()).sum().backward()
+    rtol = FP32_RTOL if dtype == torch.float32 else 1e-2
+    assert_close(out.float(), hvae_ref.apply_weight(x.double(), w.double()), rtol, "apply_weight")
+    assert_close(xd.grad.float(), xr.grad, rtol, "grad x")
+    assert_close(wd.grad.float(), wr.grad, rtol if dtype == torch.float32 else 3e-2, "grad w")
