@@ -84,7 +84,7 @@ class _BiLSTMLayer(torch.autograd.Function):
     gradients back in float32, so autograd needs no cat / cast / add nodes (and their kernels) around the layer."""
 
     @staticmethod
-    def forward(ctx, x, w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r, training, direct_grads):
+    def forward(ctx, x, w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r, training, direct_grads, after_recurrence):
         """x (B,T,In) bf16 -> y (B,T,2H) bf16."""
         B, T, In = x.shape
         H = w_hh_f.shape[1]
@@ -104,6 +104,7 @@ class _BiLSTMLayer(torch.autograd.Function):
             w_hh = torch.stack([w_hh_f, w_hh_r], 0).to(bf)
             bias_p = torch.cat([b_ih_f + b_hh_f, b_ih_r + b_hh_r], 0).to(bf)[perm]
         ctx.masters = masters if (training and direct_grads) else None
+        ctx.after_recurrence = after_recurrence
         P = torch.addmm(bias_p, x2, w_ih_p.t()).view(B, T, 2, 4 * H)         # library GEMM (time-parallel)
         y = torch.empty(B, T, 2 * H, dtype=bf, device=x.device)
         c = torch.empty(B, T, 2 * H, dtype=torch.float32, device=x.device) if training else None
@@ -126,6 +127,8 @@ class _BiLSTMLayer(torch.autograd.Function):
         L.check(L.lib().mlvae_lstm_bwd(L.ptr(gates), L.ptr(c), L.ptr(dy), L.ptr(w_hh), L.ptr(db_part), B, T, H,
                                        L.ptr(_get_scratch(B, H, x.device)), L.stream_ptr()), "mlvae_lstm_bwd")
         _probe_end("lstm_bwd", ev)
+        if ctx.after_recurrence is not None:
+            ctx.after_recurrence()                                         # e.g. start the all-reduce of the layers above
         dA = gates                                                         # now pre-activation gradients (B,T,2,H,4)
         dA2 = dA.view(B * T, 8 * H)                                        # columns in (dir, unit, gate) order
         _, inv = _gate_perm(H, x.device)
@@ -149,7 +152,7 @@ class _BiLSTMLayer(torch.autograd.Function):
                     g1 -= _mm_f32(dA[:-1, T - 1, 1].t(), y[1:, 0, H:])
             L.check(L.lib().mlvae_lstm_unpack_grads(L.ptr(dw_ih_p), L.ptr(g0), L.ptr(g1), L.ptr(db), In, H,
                                                     _ptr_array([m.grad for m in masters]), L.stream_ptr()), "mlvae_lstm_unpack_grads")
-            return (dx,) + (None,) * 10
+            return (dx,) + (None,) * 11
         dw_ih = dw_ih_p[inv]                                               # torch row order
         if T > 1:
             # dW_hh[d] = sum_{b,t} dA[b,t,d]^T h_prev[b,t,d] with h_prev the previous step IN THAT DIRECTION'S ORDER
@@ -165,12 +168,15 @@ class _BiLSTMLayer(torch.autograd.Function):
         else:
             dw_hh_f = torch.zeros(H4, H, dtype=torch.float32, device=x.device)
             dw_hh_r = torch.zeros_like(dw_hh_f)
-        return dx, dw_ih[:H4], dw_hh_f, db[:H4], db[:H4], dw_ih[H4:], dw_hh_r, db[H4:], db[H4:], None, None
+        return dx, dw_ih[:H4], dw_hh_f, db[:H4], db[:H4], dw_ih[H4:], dw_hh_r, db[H4:], db[H4:], None, None, None
 
 
-def bilstm_layer(x, w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r, training: bool, direct_grads: bool = False):
+def bilstm_layer(x, w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r, training: bool, direct_grads: bool = False,
+                 after_recurrence=None):
     """One bidirectional layer with torch's per-direction parameters (float32 masters; cast inside the layer).
     ``direct_grads``: accumulate the parameter gradients straight into the parameters' existing float32 ``.grad``
-    buffers (valid under ``loss.backward()``; the training step that owns a flat gradient bucket turns it on)."""
+    buffers (valid under ``loss.backward()``; the training step that owns a flat gradient bucket turns it on).
+    ``after_recurrence``: callable run in backward right after the recurrence kernel is enqueued, before the layer's
+    weight-gradient GEMMs."""
     return _BiLSTMLayer.apply(x.contiguous(), w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r, training,
-                              direct_grads)
+                              direct_grads, after_recurrence)

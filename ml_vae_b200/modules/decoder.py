@@ -33,7 +33,7 @@ class Decoder(nn.Module):
         self.materialize_loss = materialize_loss
         self.use_persistent_lstm = True
         self.direct_param_grads = False       # train_step.py: LSTM gradients accumulate straight into the flat bucket
-        self.top_layer_grad_hook = None      # callable(grad): runs in backward once the top LSTM layer's and the heads' gradients exist
+        self.top_layer_grad_hook = None      # callable(): runs in backward once the top LSTM layer's and the heads' gradients exist
         self._rnn_names = []
         for name, p in torch_default_lstm(self.input_size, self.hidden, self.num_layers):
             attach(self, f"rnn.{name}", p)
@@ -58,9 +58,10 @@ class Decoder(nn.Module):
             for layer in range(self.num_layers):
                 ps = [getattr(self.rnn, f"{kind}_l{layer}{sfx}") for sfx in ("", "_reverse")
                       for kind in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")]
-                if layer + 1 == self.num_layers and layer > 0 and self.top_layer_grad_hook is not None and x.requires_grad:
-                    x.register_hook(self.top_layer_grad_hook)       # train_step.py: early all-reduce of the tail of the bucket
-                x = lstm.bilstm_layer(x, *ps, training=need_grad, direct_grads=self.direct_param_grads)
+                # train_step.py (data parallel): once the backward recurrence of the layer BELOW the top one is enqueued, the
+                # gradients of the top layer and of the heads are final -> their all-reduce overlaps this layer's GEMMs
+                hook = self.top_layer_grad_hook if (layer + 2 == self.num_layers and need_grad) else None
+                x = lstm.bilstm_layer(x, *ps, training=need_grad, direct_grads=self.direct_param_grads, after_recurrence=hook)
                 if self.rnn_dropout > 0 and self.training and layer + 1 < self.num_layers:
                     x = torch.nn.functional.dropout(x, self.rnn_dropout, True)
             return x

@@ -110,10 +110,13 @@ class TrainStep:
         self.encoder.offset_dev = self.step_counter
         self._graph = None
         # Data parallel, optional (overlap_all_reduce=True): the gradients of the top LSTM layer and of the heads (the tail
-        # of the bucket, 72 % of its bytes for the benchmark recipe) exist ~1.5 ms before backward ends; their all-reduce
-        # can run on a side stream under the first layer's recurrence, the head of the bucket following after backward.
-        # Bit-identical results (tests/probes/overlap_check.py), but OFF by default: at 2 GPUs the NCCL kernel next to the
-        # latency-bound recurrence costs more than it hides (6.52 vs 6.45 ms per step, same box, A/B x2).
+        # of the bucket, 72 % of its bytes for the benchmark recipe) are final when the layer below starts its backward.
+        # Their all-reduce is issued on a side stream right AFTER that layer's recurrence kernel, so it overlaps the
+        # layer's weight-gradient GEMMs and the encoder's backward; the head of the bucket follows after backward.
+        # Bit-identical results (tests/probes/overlap_check.py), but OFF by default -- measured, same box, A/B: 6.40 vs
+        # 6.39 ms per step at 2 GPUs and 6.49 vs 6.46 ms at 8 (issued BEFORE the recurrence, next to the latency-bound
+        # kernel, it was worse still: 6.52 vs 6.45 and 6.71 vs 6.54 ms).  The 35 MB all-reduce costs ~0.3 ms at 8 GPUs
+        # and the NCCL kernel takes about as much from the kernels it runs beside as it hides.
         self._split, self._early_done, self._ar_stream = None, False, None
         top = getattr(getattr(decoder, "rnn", None), f"weight_ih_l{getattr(decoder, 'num_layers', 1) - 1}", None)
         if overlap_all_reduce and world_size > 1 and top is not None and getattr(decoder, "num_layers", 1) > 1 and hasattr(decoder, "top_layer_grad_hook"):
@@ -121,10 +124,10 @@ class TrainStep:
             self._ar_stream = torch.cuda.Stream(self.arena.flat.device)
             decoder.top_layer_grad_hook = self._early_all_reduce
 
-    def _early_all_reduce(self, _grad):
+    def _early_all_reduce(self):
         cur = torch.cuda.current_stream()
-        self._ar_stream.wait_stream(cur)                      # AccumulateGrad of the tail has been enqueued (it outranks
-        with torch.cuda.stream(self._ar_stream):              # every other ready node in the autograd engine)
+        self._ar_stream.wait_stream(cur)                      # the tail's gradients were accumulated by earlier backward nodes
+        with torch.cuda.stream(self._ar_stream):
             self.arena.all_reduce_mean(self.world_size, lo=self._split)
         self._early_done = True
         return None
