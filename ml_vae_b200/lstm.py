@@ -16,9 +16,17 @@ _scratch = {}
 PROBE = None      # bench.py sets this to a list; every recurrence launch then appends (tag, start_event, end_event)
 
 
+def max_rows_per_launch(hidden: int, device) -> int:
+    """Batch rows one cooperative launch can take: every (direction, 16-row slice, 32-unit slice) CTA must be
+    co-resident, one per SM.  Larger batches are walked in chunks of this many rows (the recurrences of different rows
+    are independent)."""
+    sms = torch.cuda.get_device_properties(device).multi_processor_count
+    return max(16, (sms // (2 * (hidden // 32))) * 16)
+
+
 def supported(x: torch.Tensor, hidden: int) -> bool:
     return x.is_cuda and x.dtype == torch.bfloat16 and hidden % 32 == 0 and 32 <= hidden <= 512 \
-        and L.lib().mlvae_lstm_scratch_bytes(x.shape[0], hidden) > 0
+        and L.lib().mlvae_lstm_scratch_bytes(min(x.shape[0], max_rows_per_launch(hidden, x.device)), hidden) > 0
 
 
 def _get_scratch(B, H, device):
@@ -109,8 +117,12 @@ class _BiLSTMLayer(torch.autograd.Function):
         y = torch.empty(B, T, 2 * H, dtype=bf, device=x.device)
         c = torch.empty(B, T, 2 * H, dtype=torch.float32, device=x.device) if training else None
         ev = _probe_start()
-        L.check(L.lib().mlvae_lstm_fwd(L.ptr(P), L.ptr(w_hh), L.ptr(y), L.ptr(c), B, T, H, int(training),
-                                       L.ptr(_get_scratch(B, H, x.device)), L.stream_ptr()), "mlvae_lstm_fwd")
+        rows = max_rows_per_launch(H, x.device)
+        for b0 in range(0, B, rows):
+            b1 = min(B, b0 + rows)
+            L.check(L.lib().mlvae_lstm_fwd(L.ptr(P[b0:b1]), L.ptr(w_hh), L.ptr(y[b0:b1]), L.ptr(c[b0:b1]) if training else None,
+                                           b1 - b0, T, H, int(training), L.ptr(_get_scratch(b1 - b0, H, x.device)), L.stream_ptr()),
+                    "mlvae_lstm_fwd")
         _probe_end("lstm_fwd", ev)
         if training:
             ctx.save_for_backward(x, w_ih_p, w_hh, P, c, y)
@@ -123,9 +135,15 @@ class _BiLSTMLayer(torch.autograd.Function):
         H = w_hh.shape[2]
         dy = dy.contiguous().to(torch.bfloat16)
         ev = _probe_start()
-        db_part = torch.empty((B + 15) // 16, 8 * H, dtype=torch.float32, device=x.device)
-        L.check(L.lib().mlvae_lstm_bwd(L.ptr(gates), L.ptr(c), L.ptr(dy), L.ptr(w_hh), L.ptr(db_part), B, T, H,
-                                       L.ptr(_get_scratch(B, H, x.device)), L.stream_ptr()), "mlvae_lstm_bwd")
+        rows = max_rows_per_launch(H, x.device)
+        db_part = torch.empty(sum((min(B, b0 + rows) - b0 + 15) // 16 for b0 in range(0, B, rows)), 8 * H, dtype=torch.float32,
+                              device=x.device)
+        part0 = 0
+        for b0 in range(0, B, rows):
+            b1 = min(B, b0 + rows)
+            L.check(L.lib().mlvae_lstm_bwd(L.ptr(gates[b0:b1]), L.ptr(c[b0:b1]), L.ptr(dy[b0:b1]), L.ptr(w_hh), L.ptr(db_part[part0:]),
+                                           b1 - b0, T, H, L.ptr(_get_scratch(b1 - b0, H, x.device)), L.stream_ptr()), "mlvae_lstm_bwd")
+            part0 += (b1 - b0 + 15) // 16
         _probe_end("lstm_bwd", ev)
         if ctx.after_recurrence is not None:
             ctx.after_recurrence()                                         # e.g. start the all-reduce of the layers above

@@ -23,7 +23,8 @@ def test_tcgen05_tile_matches_matmul(cuda, N, K, ts):
     assert rel_err(d, ref) < 2e-6
 
 
-@pytest.mark.parametrize("B,T,In,H", [(4, 6, 16, 32), (3, 1, 16, 32), (16, 20, 24, 64), (20, 33, 64, 128), (7, 40, 48, 256), (64, 60, 64, 512)])
+@pytest.mark.parametrize("B,T,In,H", [(4, 6, 16, 32), (3, 1, 16, 32), (16, 20, 24, 64), (20, 33, 64, 128), (7, 40, 48, 256), (64, 60, 64, 512),
+                                        (100, 12, 32, 512), (37, 9, 16, 384)])
 def test_persistent_lstm_layer_fwd_bwd_vs_torch(cuda, B, T, In, H):
     from ml_vae_b200.lstm import bilstm_layer
     torch.backends.cudnn.allow_tf32 = False
