@@ -57,21 +57,32 @@ norm_stats_kernel(const float *__restrict__ x, const float *__restrict__ lens, i
     }
 }
 
-__global__ void __launch_bounds__(kNormThreads)
+__global__ void __launch_bounds__(1024)
 norm_update_kernel(const float *__restrict__ mean_b, const float *__restrict__ std_b, int B, int D, int update,
                    float *__restrict__ state) {
-    // state = {count, pad[3], glob_mean[D], glob_std[D]}
+    // state = {count, pad[3], glob_mean[D], glob_std[D]}.  Column c is summed by `groups` threads over interleaved
+    // utterances, then combined in fixed group order (deterministic).
+    extern __shared__ float s_red[];            // [2][groups][D]
     float *gm = state + 4, *gs = state + 4 + D;
     const float count = state[0];
-    for (int c = threadIdx.x; c < D; c += blockDim.x) {
-        float m = 0.f, s = 0.f;
-        for (int b = 0; b < B; ++b) { m += mean_b[(size_t)b * D + c]; s += std_b[(size_t)b * D + c]; }
-        m /= (float)B; s /= (float)B;
-        if (count == 0.f) { gm[c] = m; gs[c] = s; }
+    const int groups = (int)blockDim.x / D > 0 ? (int)blockDim.x / D : 1;
+    const int c = threadIdx.x % D, g = threadIdx.x / D;
+    if (g < groups && threadIdx.x < groups * D) {
+        float m = 0.f, sd = 0.f;
+        for (int b = g; b < B; b += groups) { m += mean_b[(size_t)b * D + c]; sd += std_b[(size_t)b * D + c]; }
+        s_red[g * D + c] = m;
+        s_red[(groups + g) * D + c] = sd;
+    }
+    __syncthreads();
+    for (int col = threadIdx.x; col < D; col += blockDim.x) {
+        float m = 0.f, sd = 0.f;
+        for (int k = 0; k < groups; ++k) { m += s_red[k * D + col]; sd += s_red[(groups + k) * D + col]; }
+        m /= (float)B; sd /= (float)B;
+        if (count == 0.f) { gm[col] = m; gs[col] = sd; }
         else if (update) {
             const float w = 1.f / (count + 1.f);
-            gm[c] = (1.f - w) * gm[c] + w * m;
-            gs[c] = (1.f - w) * gs[c] + w * s;
+            gm[col] = (1.f - w) * gm[col] + w * m;
+            gs[col] = (1.f - w) * gs[col] + w * sd;
         }
     }
     __syncthreads();
@@ -110,11 +121,11 @@ int mlvae_global_norm(const float *d_x, const float *d_lens, int B, int T, int D
     cudaStream_t st = (cudaStream_t)stream;
     if (training) {
         float *mean_b = d_scratch, *std_b = d_scratch + (size_t)B * D;
-        const int threads = D > kNormThreads ? 1024 : kNormThreads;
+        const int threads = 1024;                                   // B CTAs only: as many frames in flight per CTA as possible
         const int groups = threads / D > 0 ? threads / D : 1;
         norm_stats_kernel<<<B, threads, sizeof(float) * groups * D, st>>>(d_x, d_lens, T, D, 1e-10f, mean_b, std_b);
         MLVAE_CHECK_CUDA(cudaGetLastError());
-        norm_update_kernel<<<1, kNormThreads, 0, st>>>(mean_b, std_b, B, D, update_stats, d_state);
+        norm_update_kernel<<<1, threads, sizeof(float) * 2 * groups * D, st>>>(mean_b, std_b, B, D, update_stats, d_state);
         MLVAE_CHECK_CUDA(cudaGetLastError());
     }
     const int64_t n = (int64_t)B * T * D;
