@@ -237,8 +237,8 @@ int mlvae_dense_bwd_prep(const void *d_dy, const void *d_y, void *d_g, float *d_
  * Persistent bidirectional LSTM recurrence (modules/decoder.py:14-15,22: nn.LSTM(batch_first,
  * bidirectional); one layer per call).  The input projection x W_ih^T + b_ih + b_hh for all
  * timesteps is a plain GEMM done by the caller into d_p; this entry point walks the T
- * recurrent steps of BOTH directions in one cooperative launch (tcgen05 + TMEM, W_hh
- * resident in shared memory).  bf16 only; H % 32 == 0, H <= 512.
+ * recurrent steps of BOTH directions in one cooperative launch (tcgen05; every CTA's 128 x H
+ * slice of W_hh stays resident in TENSOR MEMORY as the A operand).  bf16 only; H % 32 == 0, H <= 512.
  *   d_p   (B, T, 2, H, 4) bf16 gate pre-activations, UNIT-major with the four gates i,f,g,o of a unit
  *                             adjacent (permute the rows of W_ih / bias accordingly); when save_gates != 0
  *                             it is overwritten with the activated gates

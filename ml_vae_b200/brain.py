@@ -39,6 +39,87 @@ class EpochCounter:
         raise StopIteration
 
 
+    # Checkpointer hooks (what speechbrain's @mark_as_saver / @mark_as_loader give its EpochCounter)
+    def state_dict(self):
+        return {"current": self.current}
+
+    def load_state_dict(self, sd):
+        self.current = int(sd["current"])
+
+
+class Checkpointer:
+    """The slice of ``speechbrain.utils.checkpoints.Checkpointer`` the reference touches
+    (models/test_vanilla_vae/model.yaml:6-12, prepare_experiment.py:56, md_model.py:50-52,162-164):
+    ``recoverables`` by name, ``add_recoverable``, ``save_and_keep_only(meta, max_keys, min_keys)``,
+    ``recover_if_possible``.  Every recoverable is anything with state_dict()/load_state_dict() (modules,
+    optimisers, EpochCounter, the device-resident InputNormalization); one directory per checkpoint, one
+    ``<name>.ckpt`` (torch.save of the state_dict) per recoverable, ``meta.json`` beside them."""
+
+    def __init__(self, checkpoints_dir, recoverables=None):
+        import os
+        self.dir = os.fspath(checkpoints_dir)
+        self.recoverables = dict(recoverables or {})
+
+    def add_recoverable(self, name, obj):
+        self.recoverables[name] = obj
+
+    def _list(self):
+        import json, os
+        out = []
+        if os.path.isdir(self.dir):
+            for d in sorted(os.listdir(self.dir)):
+                m = os.path.join(self.dir, d, "meta.json")
+                if d.startswith("CKPT+") and os.path.exists(m):
+                    out.append((os.path.join(self.dir, d), json.load(open(m))))
+        return out
+
+    def save_checkpoint(self, meta=None):
+        import json, os, time
+        existing = self._list()
+        path = os.path.join(self.dir, f"CKPT+{time.strftime('%Y-%m-%d+%H-%M-%S')}+{len(existing):02d}")
+        os.makedirs(path, exist_ok=True)
+        for name, obj in self.recoverables.items():
+            torch.save(obj.state_dict(), os.path.join(path, f"{name}.ckpt"))
+        m = {k: (float(v) if hasattr(v, "__float__") else v) for k, v in (meta or {}).items()}
+        m["unixtime"] = time.time()
+        with open(os.path.join(path, "meta.json"), "w") as f:
+            json.dump(m, f)
+        return path
+
+    def save_and_keep_only(self, meta=None, max_keys=(), min_keys=(), num_to_keep=1):
+        import shutil
+        self.save_checkpoint(meta)
+        ck = self._list()
+        keep = set(p for p, _ in sorted(ck, key=lambda c: c[1]["unixtime"])[-num_to_keep:])
+        for key in max_keys:
+            c = [x for x in ck if key in x[1]]
+            keep |= set(p for p, _ in sorted(c, key=lambda x: x[1][key])[-num_to_keep:])
+        for key in min_keys:
+            c = [x for x in ck if key in x[1]]
+            keep |= set(p for p, _ in sorted(c, key=lambda x: x[1][key])[:num_to_keep])
+        for p, _ in ck:
+            if p not in keep:
+                shutil.rmtree(p, ignore_errors=True)
+
+    def recover_if_possible(self, max_key=None, min_key=None, device=None):
+        import os
+        ck = self._list()
+        if not ck:
+            return None
+        if max_key is not None:
+            ck = sorted([c for c in ck if max_key in c[1]], key=lambda c: c[1][max_key])
+        elif min_key is not None:
+            ck = sorted([c for c in ck if min_key in c[1]], key=lambda c: -c[1][min_key])
+        else:
+            ck = sorted(ck, key=lambda c: c[1]["unixtime"])
+        path, meta = ck[-1]
+        for name, obj in self.recoverables.items():
+            f = os.path.join(path, f"{name}.ckpt")
+            if os.path.exists(f):
+                obj.load_state_dict(torch.load(f, map_location=device, weights_only=False))
+        return path, meta
+
+
 class Stage:
     TRAIN, VALID, TEST = "TRAIN", "VALID", "TEST"
 
@@ -64,6 +145,9 @@ class MiniBrain:
         self.stats_loggers = {}
         self.modules.to(self.device)
         self.init_optimizers()
+        if self.checkpointer is not None:                      # md_model.py:50-52
+            for key, optimizer in self.optimizers.items():
+                self.checkpointer.add_recoverable(key, optimizer)
 
     # md_model.py:20-52
     def init_optimizers(self):

@@ -1,6 +1,6 @@
 // tcgen05 / TMEM dense projections for sm_100a.
 //   mlvae_tc05_selftest : one 128 x N x K tile through the tensor-core path (descriptor / TMEM
-//                         layout check used by tests/test_tc05_gpu.py)
+//                         layout check used by tests/test_lstm_gpu.py::test_tcgen05_tile_matches_matmul)
 //   mlvae_linear_fwd    : Y = act(X W^T + b), the building block of the FC stacks
 //                         (modules/fc_block.py:4-21, vanilla_vae.py:22-24, decoder.py:24-25)
 #include "common.cuh"
@@ -284,11 +284,8 @@ int mlvae_linear_fwd(const void *d_x, const void *d_w, const float *d_bias, void
     while (stages > 2 && (size_t)stages * st_bytes + Npad * 4 + 1024 > 200 * 1024) --stages;
     const size_t smem = (size_t)stages * st_bytes + Npad * 4 + 1024;
     LinearParams prm{(const bf16 *)d_x, (const bf16 *)d_w, d_bias, (bf16 *)d_y, M, N, K, ldx, ldy, leaky, stages};
-    static bool attr_set = false;
-    if (!attr_set) {
-        MLVAE_CHECK_CUDA(cudaFuncSetAttribute(linear_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
-    }
+    // per device and cheap: set on every call (a process-wide "done" flag would skip the second device of a process)
+    MLVAE_CHECK_CUDA(cudaFuncSetAttribute(linear_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     linear_fwd_kernel<<<(M + 127) / 128, kLinThreads, smem, (cudaStream_t)stream>>>(prm);
     MLVAE_CHECK_CUDA(cudaGetLastError());
     return MLVAE_OK;

@@ -131,6 +131,12 @@ class _BiLSTMLayer(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         x, w_ih_p, w_hh, gates, c, y = ctx.saved_tensors
+        if getattr(ctx, "consumed", False):
+            # the backward kernel overwrites the saved gates in place with the pre-activation gradients (raw pointers, so
+            # autograd's version counter cannot see it): a second backward over the same graph would read garbage
+            raise RuntimeError("bilstm_layer: backward called twice over the same forward (retain_graph / double use); "
+                               "the saved gate buffer is consumed by the first backward -- run the forward again")
+        ctx.consumed = True
         B, T, In = x.shape
         H = w_hh.shape[2]
         dy = dy.contiguous().to(torch.bfloat16)

@@ -15,6 +15,7 @@ from torch import nn
 from .. import ops
 from ..dense import linear, linear_chain
 from ._params import attach, torch_default_linear
+from .vanilla_vae import default_stream_seed
 
 
 def gumbel_softmax_hard(logits, tau: float, gumbels=None):
@@ -30,7 +31,7 @@ def gumbel_softmax_hard(logits, tau: float, gumbels=None):
 class GMMVAE(nn.Module):
     HEADS = ("prior_mean_fc", "prior_log_var_fc", "mean_fc", "log_var_fc")
 
-    def __init__(self, fc_sizes, latent_size, num_components, seed: int = 123456):
+    def __init__(self, fc_sizes, latent_size, num_components, seed: int = None):
         super().__init__()
         self.fc_sizes = [int(s) for s in fc_sizes]
         self.latent_size, self.num_components = int(latent_size), int(num_components)
@@ -45,7 +46,7 @@ class GMMVAE(nn.Module):
         w, b = torch_default_linear(self.fc_sizes[-1], self.num_components)
         attach(self, "gmm_weight_fc.weight", w)
         attach(self, "gmm_weight_fc.bias", b)
-        self.seed, self.calls = int(seed), 0
+        self.seed, self.calls = (default_stream_seed() if seed is None else int(seed)), 0
 
     def _trunk(self):
         blocks = self.fc._modules["0"].blocks._modules

@@ -16,10 +16,12 @@ from .vanilla_vae import VanillaVAE
 
 
 class HierarchicalVAE(nn.Module):
-    def __init__(self, fc_sizes, latent_size, num_components):
+    def __init__(self, fc_sizes, latent_size, num_components, seed: int = None):
         super().__init__()
-        self.vanilla_vae = VanillaVAE(fc_sizes, latent_size)            # correct pronunciation
-        self.gmm_vae = GMMVAE(fc_sizes, latent_size, num_components)    # mispronunciation
+        # two independent eps streams (h_vae.py:17-18 draws two randn_like tensors): seed / seed + 1 when given,
+        # else the per-instance defaults
+        self.vanilla_vae = VanillaVAE(fc_sizes, latent_size, seed=seed)                                   # correct pronunciation
+        self.gmm_vae = GMMVAE(fc_sizes, latent_size, num_components, seed=None if seed is None else seed + 1)  # mispronunciation
 
     def forward(self, feats, pi, eps_vanilla=None, eps_gmm=None, gumbels=None):
         van = self.vanilla_vae(feats, eps=eps_vanilla)

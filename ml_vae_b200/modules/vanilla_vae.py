@@ -22,9 +22,21 @@ from .. import ops
 from ..dense import LEAKY_SLOPE, linear_chain
 from ._params import attach, torch_default_linear
 
+_DEFAULT_SEED = 123456      # run.yaml:2
+_instances = 0              # VAE-family modules built so far in this process (construction order is deterministic)
+
+
+def default_stream_seed() -> int:
+    """Seed of the next module that was not given one: distinct per instance, so two latent blocks of one model
+    (h_vae.py:17-18 builds a VanillaVAE and a GMMVAE) never draw the same eps -- the reference draws independent
+    randn_like tensors (vanilla_vae.py:39, gmm_vae.py:53)."""
+    global _instances
+    _instances += 1
+    return _DEFAULT_SEED + (_instances - 1)
+
 
 class VanillaVAE(nn.Module):
-    def __init__(self, fc_sizes, latent_size, seed: int = 123456, materialize_loss: bool = True):
+    def __init__(self, fc_sizes, latent_size, seed: int = None, materialize_loss: bool = True):
         super().__init__()
         self.fc_sizes = [int(s) for s in fc_sizes]
         self.latent_size = int(latent_size)
@@ -37,7 +49,7 @@ class VanillaVAE(nn.Module):
             w, b = torch_default_linear(self.fc_sizes[-1], self.latent_size)
             attach(self, f"{head}.weight", w)
             attach(self, f"{head}.bias", b)
-        self.seed = int(seed)
+        self.seed = default_stream_seed() if seed is None else int(seed)
         self.calls = 0          # Philox offset: one fresh eps stream per forward
         self.offset_dev = None  # optional device int64[1] step counter used INSTEAD of `calls` (CUDA-graph replays)
 
@@ -62,7 +74,9 @@ class VanillaVAE(nn.Module):
 
     def forward(self, feats, lens=None, eps=None):
         mean, log_var = self.project(feats)
-        offset = 0 if self.offset_dev is not None else self.calls
+        # with a device step counter the kernel adds it to `offset`; the host call count moves to the high word so that
+        # repeated forwards between two counter increments (eval batches, gradient accumulation) still get fresh eps
+        offset = (self.calls << 32) if self.offset_dev is not None else self.calls
         self.calls += 1
         z, kl_elem, kl_mean = ops.reparam_kl(mean, log_var, lens=lens, eps=eps, seed=self.seed, offset=offset,
                                              want_elem=self.materialize_loss, want_mean=lens is not None,

@@ -42,6 +42,16 @@ class InputNormalization(torch.nn.Module):
     def glob_std(self):
         return None if self._state is None else self._state[4 + self._dim:4 + 2 * self._dim]
 
+    # checkpointing: the running statistics are lazily sized device state, carried as the module's extra state
+    def get_extra_state(self):
+        return {"dim": self._dim, "state": None if self._state is None else self._state.detach().cpu().clone()}
+
+    def set_extra_state(self, st):
+        self._dim = st["dim"]
+        dev = self._state.device if self._state is not None else (torch.device("cuda", torch.cuda.current_device())
+                                                                   if torch.cuda.is_available() else torch.device("cpu"))
+        self._state = None if st["state"] is None else st["state"].to(dev).clone()
+
     @torch.no_grad()
     def forward(self, x, lengths, epoch=0, out_dtype=None):
         L.require_cuda(x)

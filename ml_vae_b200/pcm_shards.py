@@ -24,6 +24,7 @@ import torch
 
 from . import _lib as L
 from .brain import PaddedBatchLite
+from .parallel import shard_bounds
 
 ALIGN = 8                      # samples; keeps every utterance 16-byte aligned for the vector loads of the unpack kernel
 _DTYPES = {"int16": np.dtype("<i2"), "float32": np.dtype("<f4")}
@@ -146,8 +147,9 @@ def batch_order(lengths, batch_size: int, sorting: str = "descending", seed: int
                 world_size: int = 1, rank: int = 0):
     """Utterance indices of every batch THIS rank sees.  ``sorting`` as run.yaml:50 (ascending | descending | random,
     applied to the duration like the reference's sorted datasets).  Under data parallelism a global batch of
-    ``batch_size * world_size`` utterances is cut into per-rank slices [r*B, (r+1)*B); a trailing global
-    batch that cannot give every rank at least one utterance is dropped."""
+    ``batch_size * world_size`` utterances is cut into balanced contiguous per-rank slices (``parallel.shard_bounds``,
+    SURVEY 8e); a trailing global batch that cannot give every rank at least one utterance is dropped, so every rank
+    sees the SAME number of batches (the gradient all-reduce of the step would hang otherwise)."""
     n = len(lengths)
     if sorting == "ascending":
         order = sorted(range(n), key=lambda i: (lengths[i], i))
@@ -163,10 +165,8 @@ def batch_order(lengths, batch_size: int, sorting: str = "descending", seed: int
         chunk = order[s:s + gb]
         if len(chunk) < gb and (drop_last or len(chunk) < world_size):
             break
-        per = -(-len(chunk) // world_size)
-        mine = chunk[rank * per:(rank + 1) * per]
-        if mine:
-            out.append(mine)
+        lo, hi = shard_bounds(len(chunk), rank, world_size)      # >= 1 utterance per rank: len(chunk) >= world_size
+        out.append(chunk[lo:hi])
     return out
 
 

@@ -22,6 +22,9 @@ Parity pinning status (see DESIGN.md "Oracle"):
   tree nor installed here, and the reference ships no feature fixtures.
   ``fbank_ref.py`` restates its published algorithm on top of ``torch.stft``;
   it is cross-checked against an independent float64 numpy DFT
-  (``fbank_np.py``) and ``torchaudio``'s mel/delta helpers where they coincide,
-  but not against SpeechBrain itself.
+  (``fbank_np.py``) and, as a third-party anchor, against ``torchaudio``'s
+  Spectrogram / AmplitudeToDB(top_db=80) / compute_deltas where the definitions
+  coincide (tests/test_oracle_golden.py::test_front_end_pieces_agree_with_torchaudio;
+  the mel matrix differs from torchaudio's by design), but not against SpeechBrain
+  itself -- so it stays "unpinned".
 """

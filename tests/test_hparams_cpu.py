@@ -86,3 +86,27 @@ def test_recipe_plugin_contract():
     assert hasattr(mod, "SBModel")
     for name in ("compute_forward", "compute_objectives", "fit_batch", "compute_and_save_losses", "init_optimizers"):
         assert callable(getattr(mod.SBModel, name))
+
+
+def test_recipe_declares_the_checkpointer_the_reference_reads(tmp_path):
+    """prepare_experiment.py:56 reads hparams['model']['checkpointer']; the stand-in saves / restores every recoverable
+    (modules by their reference state_dict keys, the epoch counter) and keeps the best checkpoint by min_key."""
+    hp = _load({"output_dir": str(tmp_path)})
+    m = hp["model"]
+    ck = m["checkpointer"]
+    assert set(ck.recoverables) >= {"encoder", "decoder", "epoch_counter"}
+    assert ck.recoverables["encoder"] is m["encoder"] and ck.recoverables["epoch_counter"] is m["epoch_counter"]
+    opt = m["optimizer"](list(m["encoder"].parameters()))
+    ck.add_recoverable("optimizer", opt)                                      # md_model.py:50-52
+    next(iter(m["epoch_counter"]))
+    want = {k: v.clone() for k, v in m["encoder"].state_dict().items()}
+    ck.save_and_keep_only(meta={"loss": 2.0}, min_keys=["loss"])
+    with torch.no_grad():
+        for p in m["encoder"].parameters():
+            p.add_(1.0)
+    m["epoch_counter"].current = 7
+    ck.save_and_keep_only(meta={"loss": 3.0}, min_keys=["loss"])             # worse: the best one must survive
+    path, meta = ck.recover_if_possible(min_key="loss")
+    assert meta["loss"] == 2.0 and m["epoch_counter"].current == 1
+    for k, v in m["encoder"].state_dict().items():
+        assert torch.equal(v, want[k]), k

@@ -151,3 +151,30 @@ def test_hvae_oracle_matches_reference_golden(tag, dtype, tol):
     close(feats.grad, "grad_feats")
     for k, p in params.items():
         close(p.grad, f"grad.{k}")
+
+
+def test_front_end_pieces_agree_with_torchaudio():
+    """Third-party anchor for the UNPINNED front-end oracle (SpeechBrain itself is absent): the three building blocks
+    whose definitions coincide with torchaudio's -- the centred, zero-padded Hamming power STFT, the power-to-dB
+    conversion with top_db = 80 and the 5-tap regression deltas with replicate padding -- are compared with
+    torchaudio.transforms.Spectrogram / AmplitudeToDB / functional.compute_deltas.  The mel matrix is NOT compared:
+    SpeechBrain's triangles (left bandwidth for both slopes) differ from torchaudio's by design."""
+    torchaudio = pytest.importorskip("torchaudio")
+    from oracle import fbank_ref
+    g = torch.Generator().manual_seed(3)
+    wav = 0.1 * torch.randn(2, 16000, generator=g, dtype=torch.float64)
+    for hop_ms, hop in ((10, 160), (20, 320)):
+        ours = fbank_ref.power_spectrum(wav, 16000, hop_ms, 25, 400)                       # (B, T, F)
+        spec = torchaudio.transforms.Spectrogram(n_fft=400, win_length=400, hop_length=hop, window_fn=torch.hamming_window,
+                                                 power=2.0, center=True, pad_mode="constant",
+                                                 wkwargs={"dtype": torch.float64})(wav)    # (B, F, T)
+        assert ours.shape == spec.transpose(1, 2).shape
+        assert float((ours - spec.transpose(1, 2)).abs().max() / spec.abs().max()) < 1e-12
+    mel = torch.rand(1, 50, 40, generator=g, dtype=torch.float64) * 10 ** (8 * torch.rand(1, 50, 40, generator=g, dtype=torch.float64) - 6)
+    ours_db = fbank_ref.amplitude_to_db(mel)
+    ta_db = torchaudio.transforms.AmplitudeToDB(stype="power", top_db=80.0)(mel)           # one "utterance": global max
+    assert float((ours_db - ta_db).abs().max()) < 1e-10
+    assert float(ours_db.min()) == pytest.approx(float(ours_db.max()) - 80.0)              # the floor is active in this case
+    d_ours = fbank_ref.deltas(ours_db)
+    d_ta = torchaudio.functional.compute_deltas(ours_db.transpose(1, 2), win_length=5, mode="replicate").transpose(1, 2)
+    assert float((d_ours - d_ta).abs().max()) < 1e-12

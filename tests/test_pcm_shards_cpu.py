@@ -90,3 +90,22 @@ def test_batch_order_sorting_and_partition():
         assert set(seen) <= set(full) and len(full) - len(seen) < world
         first = [per_rank[r][0] for r in range(world)]
         assert [i for b in first for i in b] == full[:2 * world]
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_every_rank_sees_the_same_number_of_batches(world):
+    """The step ends in an all-reduce: ranks with different batch counts would hang at the end of the epoch.
+    Every remainder n % (B * world) is covered (the ceil split left the last ranks empty)."""
+    B = 3
+    for rem in range(0, B * world):
+        n = 2 * B * world + rem
+        lengths = [(7 * i) % 23 + 1 for i in range(n)]
+        per_rank = [ps.batch_order(lengths, B, "descending", world_size=world, rank=r) for r in range(world)]
+        counts = {len(p) for p in per_rank}
+        assert len(counts) == 1, (world, rem, [len(p) for p in per_rank])
+        assert all(len(b) >= 1 for p in per_rank for b in p)
+        sizes = [len(p[-1]) for p in per_rank]
+        assert max(sizes) - min(sizes) <= 1                                      # balanced trailing batch
+        seen = [i for p in per_rank for b in p for i in b]
+        assert len(seen) == len(set(seen))
+        assert n - len(seen) == (rem if rem < world else 0)                      # only an un-shardable tail is dropped
