@@ -25,10 +25,23 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+LIBRARY_CALLS = "time-parallel GEMMs (LSTM input projection / dX / dW, dense dW) are cuBLAS through torch"
 METRIC = "train_utterances_per_sec_fwd_bwd"
 UNIT = "utt/s"
-WORKLOAD = dict(batch_per_gpu=64, seconds=5.0, sample_rate=16000, hop_ms=10, n_mels=80, deltas=False,
-                latent=64, enc_fc=64, rnn_hidden=512, rnn_layers=2, dec_fc=64)
+WORKLOADS = {
+    # BASELINE.json configs[1] (the configuration the metric is quoted on; default)
+    "c2": dict(name="BASELINE configs[1]", batch_per_gpu=64, seconds=5.0, sample_rate=16000, hop_ms=10, n_mels=80, deltas=False,
+               latent=64, enc_fc=64, rnn_hidden=512, rnn_layers=2, rnn_dropout=0.15, dec_fc=64),
+    # BASELINE.json configs[3]: long-utterance stress, 16 x 20 s (2000 frames), latent 256
+    "c4": dict(name="BASELINE configs[3]", batch_per_gpu=16, seconds=20.0, sample_rate=16000, hop_ms=10, n_mels=80, deltas=False,
+               latent=256, enc_fc=64, rnn_hidden=512, rnn_layers=2, rnn_dropout=0.15, dec_fc=64),
+}
+WORKLOAD = WORKLOADS["c2"]
+
+
+def frames_per_utt(W):
+    n, hop = int(W["seconds"] * W["sample_rate"]), int(W["sample_rate"] * W["hop_ms"] / 1000)
+    return min(1 + n // hop, (n + hop // 2) // hop)                # data_io.py:198-201 frame rule
 
 
 def peaks():
@@ -120,7 +133,8 @@ def cpu_reference_step_fn(batch: int, seed: int = 123456):
             rel = frames.float() / feats.shape[1]
             x = norm(feats, rel)
             eps = torch.randn(batch, feats.shape[1], W["latent"], generator=g)
-        loss, _ = vae_ref.recipe_loss(enc, dec, x, rel, eps, hp, W["rnn_hidden"], W["rnn_layers"])
+        # decoder.py:14-15 in training mode: nn.LSTM(dropout=0.15) with torch's own generator (timing run)
+        loss, _ = vae_ref.recipe_loss(enc, dec, x, rel, eps, hp, W["rnn_hidden"], W["rnn_layers"], torch_dropout=W["rnn_dropout"])
         loss.backward()
         torch.nn.utils.clip_grad_norm_(params, 5.0)
         opt.step()
@@ -148,25 +162,50 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    batch = 8          # bounded sample: 8 of the workload's 64 utterances per step
-    value, dt, cores = time_cpu_reference(batch, args.steps, max(args.warmup, 1))
+    # the reference's CPU path on the SAME config as our arm: the workload's full per-GPU batch every step, exactly
+    # --steps timed steps after --warmup warm-ups (~2-3 s per step on 16 host cores: K=20, W=5 ends in about a minute)
+    batch = args.batch or WORKLOAD["batch_per_gpu"]
+    steps, warm = args.steps, max(args.warmup, 1)
+    value, dt, cores = time_cpu_reference(batch, steps, warm)
     line = {"impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args.gpus, batch),
             "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{batch} x 5 s utterances per step (bounded sample of the 64-utterance batch), "
-                                       "oracle port of the reference's torch CPU path incl. restated SpeechBrain Fbank"},
+                             "sample": f"{steps} timed steps (+{warm} warm-up) of the full {batch} x {WORKLOAD['seconds']:g} s batch per step, "
+                                       "oracle port of the reference's torch CPU path (restated SpeechBrain Fbank + reference "
+                                       "VAE modules, LSTM dropout 0.15, fwd+bwd+clip+Adam), fp32, all host cores"},
             "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
 
+def _traffic_record(config):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernels at the benched shape, taken from ONE
+    `ncu --set full` capture committed under profiles/ (profiles/r02_lstm_traffic.json, written by profiles/lstm_traffic.py)."""
+    p = os.path.join(ROOT, "profiles", "r02_lstm_traffic.json")
+    if not os.path.exists(p):
+        return None
+    return json.load(open(p)).get(config)
+
+
+def measured_traffic(config):
+    r = _traffic_record(config)
+    return None if r is None else r["dram_bytes_per_launch"]
+
+
+def traffic_source(config):
+    r = _traffic_record(config)
+    return None if r is None else r["source"]
+
+
 def workload_config(n_gpus, batch_per_gpu):
     W = WORKLOAD
-    return {"workload": f"BASELINE configs[1]: {batch_per_gpu} x {W['seconds']:g} s 16 kHz utterances per GPU -> "
-                        f"{W['n_mels']}-dim fbank (hop {W['hop_ms']} ms, T=500) -> VanillaVAE(64-64, latent {W['latent']}) -> "
-                        f"Decoder(biLSTM {W['rnn_layers']}x{W['rnn_hidden']} + heads) -> KL + NLL, fwd+bwd+Adam",
-            "global_batch": batch_per_gpu * n_gpus, "frames_per_utt": 500, "parallelism": f"dp{n_gpus}",
+    T = frames_per_utt(W)
+    return {"workload": f"{W['name']}: {batch_per_gpu} x {W['seconds']:g} s 16 kHz utterances per GPU -> "
+                        f"{W['n_mels']}-dim fbank (hop {W['hop_ms']} ms, T={T}) -> VanillaVAE(64-64, latent {W['latent']}) -> "
+                        f"Decoder(biLSTM {W['rnn_layers']}x{W['rnn_hidden']}, inter-layer dropout {W['rnn_dropout']} + heads) -> "
+                        f"KL + NLL, fwd+bwd+clip+Adam",
+            "global_batch": batch_per_gpu * n_gpus, "frames_per_utt": T, "parallelism": f"dp{n_gpus}",
             "l2": "256 MiB flush write between timed steps (outside the event pairs)"}
 
 
@@ -202,7 +241,8 @@ def run_ours(args):
     torch.manual_seed(123456)                                   # run.yaml:2-3
     fb = Fbank(deltas=W["deltas"], sample_rate=W["sample_rate"], hop_length=W["hop_ms"], n_fft=400, n_mels=W["n_mels"])
     enc = VanillaVAE([D, W["enc_fc"], W["enc_fc"]], W["latent"]).to(dev)
-    dec = Decoder(W["latent"], W["rnn_hidden"], W["rnn_layers"], 0.0, [2 * W["rnn_hidden"], W["dec_fc"], W["dec_fc"], D]).to(dev)
+    dec = Decoder(W["latent"], W["rnn_hidden"], W["rnn_layers"], W["rnn_dropout"],
+                  [2 * W["rnn_hidden"], W["dec_fc"], W["dec_fc"], D]).to(dev)
     ts = TrainStep(fb, InputNormalization().to(dev), enc, dec, {"kld_weight": 0.001, "batch_size": B}, lr=1e-3,
                    compute_dtype=dtype, world_size=world, overlap_all_reduce=args.overlap)
 
@@ -320,11 +360,12 @@ def run_ours(args):
     pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
     tflops_peak = float(pk.get("bf16_tflops_sustained", 1400.0))
     step_ms = sec / args.steps * 1e3
-    T_frames, H = 500, W["rnn_hidden"]
+    T_frames, H = frames_per_utt(W), W["rnn_hidden"]
+    fb_bytes = B * n * 4 + B * T_frames * D * 4
     kernels = {"fbank(memset+logmel+finish)": {"ms_per_launch": round(fb_ms, 5), "launches_per_step": 1, "bound": "hbm",
-                                                "algorithmic_bytes": B * n * 4 + B * 500 * D * 4,
-                                                "achieved_gbs": round((B * n * 4 + B * 500 * D * 4) / (fb_ms * 1e-3) / 1e9, 1),
-                                                "frac_of_hbm_peak": round((B * n * 4 + B * 500 * D * 4) / (fb_ms * 1e-3) / 1e9 / peak, 4),
+                                                "algorithmic_bytes": fb_bytes,
+                                                "achieved_gbs": round(fb_bytes / (fb_ms * 1e-3) / 1e9, 1),
+                                                "frac_of_hbm_peak": round(fb_bytes / (fb_ms * 1e-3) / 1e9 / peak, 4),
                                                 "share_of_step": round(fb_ms / step_ms, 4)}}
     if lstm_ms:
         # dominant hand-written kernels: the persistent LSTM recurrences (one launch per layer and pass, both directions)
@@ -341,13 +382,15 @@ def run_ours(args):
                                         "share_of_step": round(sum(vs) / probe_steps / step_ms, 4)}
         roof = {"bound": "tensor", "kernel": "persistent biLSTM recurrence (lstm_fwd_kernel + lstm_bwd_kernel, tcgen05 + TMEM-resident W_hh)",
                 "achieved": round(flops / (per_launch * 1e-3) / 1e12, 1), "peak": tflops_peak, "unit": "TFLOP/s",
-                "frac": round(flops / (per_launch * 1e-3) / 1e12 / tflops_peak, 4), "traffic": 383.2e6 * T_frames / 300,
+                "frac": round(flops / (per_launch * 1e-3) / 1e12 / tflops_peak, 4), "traffic": measured_traffic(args.config),
                 "peak_source": "measured bf16_tflops_sustained (MEASURED_PEAKS.json)", "algorithmic_flops_per_launch": flops,
                 "ms_per_launch": round(per_launch, 4), "share_of_step": round(per_step / step_ms, 4),
-                "note": "latency-bound by construction: T=500 dependent timesteps per launch (1.9-2.3 us each: L2 exchange of h_t + "
+                "note": f"latency-bound by construction: T={T_frames} dependent timesteps per launch (L2 exchange of h_t + "
                         "32 small MMAs + gate math); the roofline fraction is low because the recurrence exposes only "
                         "64x2048x512 MACs of parallelism per step, not because of wasted traffic (ncu: dram bytes = P + gates + "
-                        "cell states + outputs, no re-reads; profiles/r01_lstm_final_ncu_raw.csv: 383 MB per forward launch at T=300, scaled to T=500 here). cuDNN's bf16 path takes 9x longer."}
+                        "cell states + outputs, no re-reads; `traffic` = dram read+write bytes per launch from the ncu --set full "
+                        "capture of this shape named in traffic_source, null until one is committed). cuDNN's bf16 path takes 9x longer.",
+                "traffic_source": traffic_source(args.config)}
     else:
         roof = {"bound": "hbm", "kernel": "fused fbank front-end", "achieved": kernels["fbank(memset+logmel+finish)"]["achieved_gbs"],
                 "peak": peak, "unit": "GB/s", "frac": kernels["fbank(memset+logmel+finish)"]["frac_of_hbm_peak"], "traffic": None,
@@ -360,14 +403,15 @@ def run_ours(args):
             "e2e": {"value": round(e2e, 2), "unit": UNIT, "h2d_bytes_per_step": B * n * 4 * world,
                     "d2h_bytes_per_step": 4 * world, "ms_per_step": round(sec_e2e / args.steps * 1e3, 4)},
             "gpu_launches": int(round(launches)), "roofline": roof, "kernels": kernels,
-            "library_calls": "time-parallel GEMMs (LSTM input projection / dX / dW, dense heads) are cuBLAS through torch in round 1",
+            "library_calls": LIBRARY_CALLS,
             "clocks": clocks, "wall_s": round(wall, 3), "cuda_graph": graphed}
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
-            v, dt, cores = time_cpu_reference(8, 2, 1)
+            v, dt, cores = time_cpu_reference(B, 3, 1)
             line["cpu_baseline"] = {"value": round(v, 3), "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": "8 x 5 s utterances per step, 1 warm-up + 2 timed fwd+bwd+Adam steps of "
-                                              "the oracle port (restated SpeechBrain Fbank + reference VAE modules), fp32"}
+                                    "sample": f"full {B} x {W['seconds']:g} s batch per step, 1 warm-up + 3 timed fwd+bwd+clip+Adam steps "
+                                              "of the oracle port (restated SpeechBrain Fbank + reference VAE modules, LSTM dropout "
+                                              "0.15), fp32, all host cores"}
         emit(line)
     if world > 1:
         # release the captured graph (it references the communicator) before tearing the process group down, and do
@@ -408,11 +452,14 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--config", default="c2", choices=sorted(WORKLOADS), help="c2 = BASELINE configs[1] (default), c4 = configs[3]")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", default="", help="write a torch.profiler kernel table of 3 steps to this path")
     ap.add_argument("--no-graph", action="store_true", help="do not capture the step in a CUDA graph")
     ap.add_argument("--overlap", action="store_true", help="all-reduce the tail of the gradient bucket under the first LSTM layer's backward (measured slower at N=2)")
     args = ap.parse_args()
+    global WORKLOAD
+    WORKLOAD = WORKLOADS[args.config]
     quiet_stdout()
     if args.impl == "reference":
         run_reference(args)

@@ -234,6 +234,17 @@ int mlvae_dense_bwd_prep(const void *d_dy, const void *d_y, void *d_g, float *d_
                          void *d_scratch, void *stream);
 
 /* ------------------------------------------------------------------------- *
+ * Inter-layer dropout of the stacked LSTM (modules/decoder.py:14-15: nn.LSTM(..., dropout=rnn_dropout),
+ * models/test_vanilla_vae/model.yaml dec_rnn_dropout: 0.15), with a reproducible counter-based mask instead
+ * of torch's stateful generator.  y = keep ? x / (1 - p) : 0; element i keeps iff the 16-bit lane i % 8
+ * (word (i%8)/2, low half first) of Philox4x32-10(counter = (i/8, offset [+ *d_offset_add]), key = seed) is
+ * >= round(p * 65536) (host restatement: oracle/philox_ref.py dropout_keep_mask).  The same call on dy is the
+ * backward.  In-place (d_y == d_x) is allowed.  dtype MLVAE_F32 | MLVAE_BF16; buffers 16-byte aligned.
+ * ------------------------------------------------------------------------- */
+int mlvae_dropout(const void *d_x, void *d_y, int64_t n, float p, uint64_t seed, uint64_t offset,
+                  const uint64_t *d_offset_add, int dtype, void *stream);
+
+/* ------------------------------------------------------------------------- *
  * Persistent bidirectional LSTM recurrence (modules/decoder.py:14-15,22: nn.LSTM(batch_first,
  * bidirectional); one layer per call).  The input projection x W_ih^T + b_ih + b_hh for all
  * timesteps is a plain GEMM done by the caller into d_p; this entry point walks the T

@@ -58,6 +58,7 @@ SIGNATURES = {
     "mlvae_lstm_unpack_grads": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "mlvae_pcm_unpack": (_i, [_vp, _i, _vp, _vp, _i, _i64, C.c_float, _vp, _vp]),
     "mlvae_tc05_selftest": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "mlvae_dropout": (_i, [_vp, _vp, _i64, C.c_float, _u64, _u64, _vp, _i, _vp]),
     "mlvae_fbank_fwd": (_i, [_vp, _vp, _vp, _i, _i64, _i64, _i, _vp, _i, _i, _vp, _vp, _vp]),
 }
 

@@ -32,6 +32,11 @@ class Decoder(nn.Module):
         self.loss_type = loss_type
         self.materialize_loss = materialize_loss
         self.use_persistent_lstm = True
+        # inter-layer dropout mask: counter-based Philox stream (csrc/dropout.cu) keyed by (seed, call count, layer)
+        # [+ a device step counter when the training step is replayed as a CUDA graph]
+        self.dropout_seed = 123456 ^ 0x5DEECE66D
+        self.dropout_calls = 0
+        self.dropout_offset_dev = None
         self.direct_param_grads = False       # train_step.py: LSTM gradients accumulate straight into the flat bucket
         self.top_layer_grad_hook = None      # callable(): runs in backward once the top LSTM layer's and the heads' gradients exist
         self._rnn_names = []
@@ -63,12 +68,31 @@ class Decoder(nn.Module):
                 hook = self.top_layer_grad_hook if (layer + 2 == self.num_layers and need_grad) else None
                 x = lstm.bilstm_layer(x, *ps, training=need_grad, direct_grads=self.direct_param_grads, after_recurrence=hook)
                 if self.rnn_dropout > 0 and self.training and layer + 1 < self.num_layers:
-                    x = torch.nn.functional.dropout(x, self.rnn_dropout, True)
+                    x = ops.dropout(x, self.rnn_dropout, self.dropout_seed, self._dropout_offset(layer), self.dropout_offset_dev)
+            if self.rnn_dropout > 0 and self.training:
+                self.dropout_calls += 1
+            return x
+        z = x.new_zeros(2, x.shape[0], self.hidden)
+        if self.rnn_dropout > 0 and self.training and self.num_layers > 1:
+            # library LSTM one layer at a time with OUR counter-based dropout between the layers (cuDNN's own dropout draws
+            # from a stateful generator nothing else can reproduce)
+            for layer in range(self.num_layers):
+                flat = [getattr(self.rnn, f"{kind}_l{layer}{sfx}").to(x.dtype) for sfx in ("", "_reverse")
+                        for kind in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")]
+                x, _, _ = torch._VF.lstm(x, (z, z), flat, True, 1, 0.0, self.training, True, True)
+                if layer + 1 < self.num_layers:
+                    x = ops.dropout(x, self.rnn_dropout, self.dropout_seed, self._dropout_offset(layer), self.dropout_offset_dev)
+            self.dropout_calls += 1
             return x
         flat = [getattr(self.rnn, n).to(x.dtype) for n in self._rnn_names]
         z = x.new_zeros(2 * self.num_layers, x.shape[0], self.hidden)
-        out, _, _ = torch._VF.lstm(x, (z, z), flat, True, self.num_layers, self.rnn_dropout, self.training, True, True)
+        out, _, _ = torch._VF.lstm(x, (z, z), flat, True, self.num_layers, 0.0, self.training, True, True)
         return out
+
+    def _dropout_offset(self, layer: int) -> int:
+        # low word = device step counter (added by the kernel when present), high word = host call count and layer
+        k = self.dropout_calls * self.num_layers + layer
+        return (k << 32) if self.dropout_offset_dev is not None else k
 
     def forward(self, sampled_h, target_feats, lens=None):
         if self.loss_type not in ("likelihood", "mse"):

@@ -256,3 +256,33 @@ class _MaskedReduce(torch.autograd.Function):
 
 def masked_reduce(loss, lens, reduction: str = "mean"):
     return _MaskedReduce.apply(loss, lens, reduction)
+
+
+class _Dropout(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, p, seed, offset, offset_dev):
+        L.require_cuda(x)
+        x = x.contiguous()
+        y = torch.empty_like(x)
+        L.check(L.lib().mlvae_dropout(L.ptr(x), L.ptr(y), x.numel(), float(p), seed, offset, L.ptr(offset_dev), L.dtype_code(x),
+                                      L.stream_ptr()), "mlvae_dropout")
+        ctx.args = (float(p), seed, offset, offset_dev)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        p, seed, offset, offset_dev = ctx.args
+        dy = dy.contiguous()
+        dx = torch.empty_like(dy)
+        L.check(L.lib().mlvae_dropout(L.ptr(dy), L.ptr(dx), dy.numel(), p, seed, offset, L.ptr(offset_dev), L.dtype_code(dy),
+                                      L.stream_ptr()), "mlvae_dropout")
+        return dx, None, None, None, None
+
+
+def dropout(x: torch.Tensor, p: float, seed: int, offset: int = 0, offset_dev=None) -> torch.Tensor:
+    """Counter-based dropout (csrc/dropout.cu): y = keep ? x / (1 - p) : 0 with the Philox mask of (seed, offset
+    [+ offset_dev[0], a device int64 step counter]); the backward regenerates the mask.  Stands in for the inter-layer
+    dropout of nn.LSTM (modules/decoder.py:14-15)."""
+    if p <= 0.0:
+        return x
+    return _Dropout.apply(x, p, int(seed), int(offset), offset_dev)

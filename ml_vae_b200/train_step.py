@@ -108,6 +108,9 @@ class TrainStep:
         # draws fresh eps on every replay
         self.step_counter = torch.zeros(1, dtype=torch.int64, device=self.arena.flat.device)
         self.encoder.offset_dev = self.step_counter
+        if hasattr(self.decoder, "dropout_offset_dev"):
+            self.decoder.dropout_offset_dev = self.step_counter     # fresh inter-layer dropout mask on every graph replay
+            self.decoder.dropout_seed = (seed ^ 0x5DEECE66D) & 0xFFFFFFFFFFFFFFFF
         self._graph = None
         # Data parallel, optional (overlap_all_reduce=True): the gradients of the top LSTM layer and of the heads (the tail
         # of the bucket, 72 % of its bytes for the benchmark recipe) are final when the layer below starts its backward.

@@ -75,3 +75,22 @@ def philox_normal(seed: int, offset: int, n: int, dtype=np.float32) -> np.ndarra
     rad = np.sqrt(-2.0 * np.log(u1))
     out = np.stack([rad * np.cos(theta), rad * np.sin(theta)], -1)
     return out.reshape(-1)[:n].astype(dtype)
+
+
+def dropout_keep_mask(seed: int, offset: int, n: int, p: float) -> np.ndarray:
+    """Keep mask (bool, n) of the inter-layer LSTM dropout (decoder.py:14-15, dropout=rnn_dropout) as the CUDA kernel
+    csrc/dropout.cu draws it: element i uses the 16-bit lane i % 8 (word (i % 8) // 2, low half first) of the Philox
+    block with counter (i // 8, offset) and key seed; keep iff u16 >= round(p * 65536).  The kept values are scaled by
+    float32(1 / (1 - p)), like torch.nn.functional.dropout."""
+    nblk = (n + 7) // 8
+    q = np.arange(nblk, dtype=np.uint64)
+    ctr = np.stack([q & MASK, q >> np.uint64(32),
+                    np.full(nblk, offset & 0xFFFFFFFF, np.uint64),
+                    np.full(nblk, (offset >> 32) & 0xFFFFFFFF, np.uint64)], -1).astype(np.uint32)
+    key = np.empty((nblk, 2), np.uint32)
+    key[:, 0] = seed & 0xFFFFFFFF
+    key[:, 1] = (seed >> 32) & 0xFFFFFFFF
+    w = philox4x32_10(ctr, key)                                   # (nblk, 4)
+    u16 = np.stack([w & np.uint32(0xFFFF), w >> np.uint32(16)], -1).reshape(nblk * 8)[:n]
+    thresh = int(np.rint(np.float32(p) * np.float32(65536.0)))
+    return u16 >= thresh

@@ -77,22 +77,36 @@ def recon_elementwise(mean, log_var, target, loss_type: str = "likelihood"):
     raise ValueError(f"Invalid loss type: {loss_type}")
 
 
-def bilstm(params: dict, x, hidden: int, num_layers: int):
-    """decoder.py:14-15,22: batch_first bidirectional LSTM, dropout disabled."""
-    flat = []
-    for layer in range(num_layers):
+def bilstm(params: dict, x, hidden: int, num_layers: int, drop_masks=None, drop_p: float = 0.0, torch_dropout: float = 0.0):
+    """decoder.py:14-15,22: batch_first bidirectional LSTM.  ``drop_masks`` (list of num_layers - 1 boolean keep masks of
+    shape (B, T, 2*hidden)) injects the inter-layer dropout nn.LSTM(dropout=p) applies in training mode to the output of
+    every layer but the last: out * keep / (1 - p).  None = dropout disabled (eval mode / p = 0).  ``torch_dropout`` > 0
+    runs the stacked LSTM in training mode with torch's own (irreproducible) dropout: timing runs only."""
+    def layer_params(layer):
+        flat = []
         for sfx in ("", "_reverse"):
             flat += [params[f"rnn.weight_ih_l{layer}{sfx}"], params[f"rnn.weight_hh_l{layer}{sfx}"],
                      params[f"rnn.bias_ih_l{layer}{sfx}"], params[f"rnn.bias_hh_l{layer}{sfx}"]]
-    z = x.new_zeros(2 * num_layers, x.shape[0], hidden)
-    out, _, _ = torch._VF.lstm(x, (z, z), flat, True, num_layers, 0.0, False, True, True)
+        return flat
+    z = x.new_zeros(2, x.shape[0], hidden)
+    if drop_masks is None:
+        flat = [p for layer in range(num_layers) for p in layer_params(layer)]
+        zz = x.new_zeros(2 * num_layers, x.shape[0], hidden)
+        out, _, _ = torch._VF.lstm(x, (zz, zz), flat, True, num_layers, float(torch_dropout), torch_dropout > 0, True, True)
+        return out
+    out = x
+    for layer in range(num_layers):
+        out, _, _ = torch._VF.lstm(out, (z, z), layer_params(layer), True, 1, 0.0, False, True, True)
+        if layer + 1 < num_layers:
+            scale = torch.tensor(1.0, dtype=torch.float32) / (1.0 - torch.tensor(drop_p, dtype=torch.float32))
+            out = out * drop_masks[layer].to(out.dtype) * scale.to(out.dtype)
     return out
 
 
 def decoder_forward(params: dict, sampled_h, target, hidden: int = 512, num_layers: int = 2,
-                    loss_type: str = "likelihood"):
-    """Decoder.forward (decoder.py:21-35), rnn dropout = 0."""
-    r = bilstm(params, sampled_h, hidden, num_layers)
+                    loss_type: str = "likelihood", drop_masks=None, drop_p: float = 0.0, torch_dropout: float = 0.0):
+    """Decoder.forward (decoder.py:21-35); rnn dropout off unless keep masks are injected."""
+    r = bilstm(params, sampled_h, hidden, num_layers, drop_masks, drop_p, torch_dropout)
     mean = fc_stack(params, "mean_fc.blocks", r)
     log_var = fc_stack(params, "log_var_fc.blocks", r)
     return {"mean": mean, "log_var": log_var, "rnn_out": r,
@@ -141,11 +155,12 @@ def weighted_total(losses: dict, hparams: dict):
 
 
 def recipe_loss(enc_params: dict, dec_params: dict, feats, lens, eps, hparams: dict,
-                hidden: int = 512, num_layers: int = 2):
+                hidden: int = 512, num_layers: int = 2, drop_masks=None, drop_p: float = 0.0, torch_dropout: float = 0.0):
     """test_vanilla_vae compute_forward + compute_objectives (model.py:19-55)
     after the normalizer: returns (loss, parts dict)."""
     enc = encoder_forward(enc_params, feats, eps)
-    dec = decoder_forward(dec_params, enc["sampled_h"], feats, hidden, num_layers)
+    dec = decoder_forward(dec_params, enc["sampled_h"], feats, hidden, num_layers, drop_masks=drop_masks, drop_p=drop_p,
+                          torch_dropout=torch_dropout)
     losses = {"kld_loss": masked_reduce(enc["loss"], lens),
               "recon_loss": masked_reduce(dec["losses"]["recon_loss"], lens)}
     return weighted_total(losses, hparams), {"enc": enc, "dec": dec, "losses": losses}

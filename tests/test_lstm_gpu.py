@@ -24,7 +24,10 @@ def test_tcgen05_tile_matches_matmul(cuda, N, K, ts):
 
 
 @pytest.mark.parametrize("B,T,In,H", [(4, 6, 16, 32), (3, 1, 16, 32), (16, 20, 24, 64), (20, 33, 64, 128), (7, 40, 48, 256), (64, 60, 64, 512),
-                                        (100, 12, 32, 512), (37, 9, 16, 384)])
+                                        (100, 12, 32, 512), (37, 9, 16, 384),
+                                        # BASELINE configs[1] (64 x 5 s, T = 500) and configs[3] (16 x 20 s, T = 2000, latent 256): both
+                                        # layers of the decoder's biLSTM (In = latent, In = 2H), forward + every gradient at full length
+                                        (64, 500, 64, 512), (64, 500, 1024, 512), (16, 2000, 256, 512), (16, 2000, 1024, 512)])
 def test_persistent_lstm_layer_fwd_bwd_vs_torch(cuda, B, T, In, H):
     from ml_vae_b200.lstm import bilstm_layer
     torch.backends.cudnn.allow_tf32 = False
@@ -56,7 +59,7 @@ def test_persistent_lstm_layer_fwd_bwd_vs_torch(cuda, B, T, In, H):
 
 def test_decoder_uses_persistent_lstm_in_bf16_and_matches_cudnn(cuda):
     """Whole decoder (2 x biLSTM + heads + fused NLL) in bf16 on the persistent kernels, against the float32
-    cuDNN path as the reference; it must stay within 3e-2 (or twice the error of cuDNN own bf16 path) on loss and weight gradients."""
+    cuDNN path as the reference; loss and weight gradients within the bf16 tolerance (1e-2 rel-to-max)."""
     from ml_vae_b200.modules import Decoder
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -79,7 +82,7 @@ def test_decoder_uses_persistent_lstm_in_bf16_and_matches_cudnn(cuda):
     lib = run(False, torch.bfloat16)
     for a, b, r, name in zip(ours, lib, ref, ["loss", "dW_hh_l1", "dW_ih_l0", "dW_head"]):
         e_ours, e_lib = rel_err(a, r), rel_err(b, r)
-        assert e_ours <= max(3e-2, 2.0 * e_lib), (name, e_ours, e_lib)
+        assert e_ours <= BF16_RTOL, (name, e_ours, e_lib)
 
 
 def test_unsupported_hidden_size_is_refused(cuda):

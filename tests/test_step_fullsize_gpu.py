@@ -1,0 +1,88 @@
+"""GPU: ONE whole bf16 training step (fused fbank -> normaliser -> VanillaVAE -> Decoder with inter-layer dropout 0.15
+-> masked KL + NLL -> backward) at the BENCHMARK shapes against the CPU oracle in float32 on the same audio, the same
+eps and the same dropout masks:
+  configs[1]  64 x 5 s  -> T = 500,  latent 64   (the bench.py workload)
+  configs[3]  16 x 20 s -> T = 2000, latent 256  (long-utterance stress)
+Tolerance: the bf16 bar of BASELINE.json (1e-2): loss relative, every parameter-gradient tensor rel-to-max.
+The oracle step takes a few seconds on the host cores."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from _util import BF16_RTOL, rel_err
+from conftest import ROOT
+from oracle import fbank_ref, philox_ref, vae_ref
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(cuda, B, seconds, latent, p_drop, seed=1234):
+    from ml_vae_b200 import ops
+    from ml_vae_b200.features import Fbank
+    from ml_vae_b200.modules import Decoder, VanillaVAE
+    from ml_vae_b200.normalizer import InputNormalization
+    from ml_vae_b200.train_step import TrainStep
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(123456)
+    n, D, H = int(seconds * 16000), 80, 512
+    g = torch.Generator().manual_seed(B + n)
+    lens_abs = (n * (0.5 + 0.5 * torch.rand(B, generator=g))).long() // 160 * 160
+    lens_abs[0] = n
+    lens_abs, _ = torch.sort(lens_abs, descending=True)                      # run.yaml:50 sorting: descending
+    wav = torch.zeros(B, n)
+    for b in range(B):
+        wav[b, : lens_abs[b]] = 0.1 * torch.randn(int(lens_abs[b]), generator=g)
+    enc = VanillaVAE([D, 64, 64], latent).to(cuda)
+    dec = Decoder(latent, H, 2, p_drop, [2 * H, 64, 64, D]).to(cuda)
+    enc_sd = {k: v.detach().cpu().clone() for k, v in enc.state_dict().items()}
+    dec_sd = {k: v.detach().cpu().clone() for k, v in dec.state_dict().items()}
+    hp = {"kld_weight": 0.001, "batch_size": B}
+    ts = TrainStep(Fbank(deltas=False, hop_length=10, n_mels=80), InputNormalization().to(cuda), enc, dec, hp,
+                   compute_dtype=torch.bfloat16, seed=seed)
+    feats, rel = ts.features(wav.to(cuda), lens_abs.to(cuda))
+    loss, kld, rec = ts.losses(feats, rel)
+    loss.backward()
+    torch.cuda.synchronize()
+    T = feats.shape[1]
+
+    # ---- oracle: float32 on the host, identical audio / eps / dropout mask ----
+    torch.set_num_threads(os.cpu_count() or 1)
+    f_ref, frames = fbank_ref.batched_features(wav, lens_abs, deltas_=False, hop_length=10, n_mels=80)
+    assert f_ref.shape[1] == T
+    rel_ref = frames.float() / T
+    x = vae_ref.GlobalNormRef()(f_ref, rel_ref)
+    eps = ops.philox_normal((B, T, latent), seed, 0).cpu()
+    masks = None
+    if p_drop > 0:
+        keep = philox_ref.dropout_keep_mask(dec.dropout_seed, 0, B * T * 2 * H, p_drop).reshape(B, T, 2 * H)
+        masks = [torch.from_numpy(keep)]
+    ep = {k: v.clone().requires_grad_(True) for k, v in enc_sd.items()}
+    dp = {k: v.clone().requires_grad_(True) for k, v in dec_sd.items()}
+    ref_loss, parts = vae_ref.recipe_loss(ep, dp, x, rel_ref, eps, hp, H, 2, drop_masks=masks, drop_p=p_drop)
+    ref_loss.backward()
+
+    errs = {"loss": abs(float(loss) - float(ref_loss)) / abs(float(ref_loss)),
+            "kld_loss": abs(float(kld) - float(parts["losses"]["kld_loss"])) / abs(float(parts["losses"]["kld_loss"])),
+            "recon_loss": abs(float(rec) - float(parts["losses"]["recon_loss"])) / abs(float(parts["losses"]["recon_loss"]))}
+    for k, prm in enc.named_parameters():
+        errs[f"grad enc.{k}"] = rel_err(prm.grad, ep[k].grad)
+    for k, prm in dec.named_parameters():
+        errs[f"grad dec.{k}"] = rel_err(prm.grad, dp[k].grad)
+    errs["feats(bf16, normalised)"] = rel_err(feats.float(), x)
+    return errs, {"B": B, "T": T, "latent": latent, "dropout": p_drop, "loss": float(loss), "oracle_loss": float(ref_loss)}
+
+
+@pytest.mark.parametrize("name,B,seconds,latent,p_drop", [("configs1", 64, 5.0, 64, 0.15), ("configs3", 16, 20.0, 256, 0.15),
+                                                         ("configs1_nodrop", 64, 5.0, 64, 0.0)])
+def test_whole_bf16_step_matches_oracle_at_benchmark_shape(cuda, name, B, seconds, latent, p_drop):
+    errs, meta = _run(cuda, B, seconds, latent, p_drop)
+    out = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(out):                       # evidence for profiles/: every error of the step, not just pass / fail
+        with open(os.path.join(out, f"step_parity_{name}.json"), "w") as f:
+            json.dump({"meta": meta, "rel_err": errs}, f, indent=1)
+    bad = {k: v for k, v in errs.items() if not (v <= BF16_RTOL)}
+    assert not bad, (meta, bad)
