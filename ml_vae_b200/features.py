@@ -128,4 +128,7 @@ class Fbank(torch.nn.Module):
                                         L.stream_ptr()), "mlvae_fbank_fwd", kernels=2)
         if wav_lens is None and not truncate:
             return out
-        return out, frames.float() / t_out
+        # relative lengths exactly as the host pipeline forms them (IEEE float32 division): torch's CUDA division by a python
+        # SCALAR multiplies by the reciprocal, which is 1 ulp off for some lengths and moves the reference's mask predicate
+        # t < lens * T (data_utils.py:88) by one frame; tensor / tensor divides correctly rounded
+        return out, frames.float() / torch.full((B,), float(t_out), dtype=torch.float32, device=wav.device)

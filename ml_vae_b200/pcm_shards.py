@@ -244,7 +244,7 @@ class PcmBatchLoader:
         feats, rel = self.fbank(wav, d_len, truncate=True, out_dtype=self.out_dtype)
         batch = PaddedBatchLite({"id": [self.reader.utts[i]["id"] for i in idxs], "feat": (feats, rel), "wav_len": d_len})
         if self.keep_wav:
-            batch["wav"] = (wav, d_len.float() / float(n_max))
+            batch["wav"] = (wav, d_len.float() / torch.full_like(d_len, n_max, dtype=torch.float32))   # exact IEEE division (see features.py)
         return batch
 
     def __iter__(self):

@@ -142,3 +142,23 @@ def test_internal_tables_match_torch(cuda):
     fb._get_plan(wav.device)        # re-upload this module's tables (constant memory is shared)
     fb._destroy()
     assert (out - a).abs().max() < 1e-3
+
+
+def test_relative_lengths_are_ieee_divisions(cuda):
+    """The (feat, rel_lens) pair feeds the reference's mask predicate t < rel * T (data_utils.py:88), which is exact only if
+    rel is the correctly rounded float32 quotient frames / T the host pipeline would form.  torch's CUDA division by a
+    python scalar multiplies by the reciprocal (1 ulp off for some lengths -> the mask moves by one frame)."""
+    from ml_vae_b200.features import Fbank
+    fb = Fbank(deltas=False, hop_length=10, n_mels=40)
+    N = 160 * 500
+    lens = torch.arange(160, N + 1, 160 * 7, dtype=torch.int32)
+    wav = torch.zeros(len(lens), N, device=cuda)
+    _, rel = fb(wav, lens.to(cuda), truncate=True)
+    frames = torch.tensor([fb.frames(int(n), True) for n in lens], dtype=torch.float32)
+    want = frames / 500.0                                            # CPU: IEEE division
+    assert torch.equal(rel.cpu(), want)
+    # and therefore the same mask as the reference's predicate on host-computed lengths (which itself keeps one frame more
+    # than `frames` where float32(frames / T) * T rounds up, e.g. 127 / 500 -- SURVEY 8a-9; that quirk is reproduced, not fixed)
+    mask_ours = torch.arange(500, dtype=torch.float32)[None] < (rel.cpu() * 500)[:, None]
+    mask_ref = torch.arange(500, dtype=torch.float32)[None] < (want * 500)[:, None]
+    assert torch.equal(mask_ours, mask_ref)
