@@ -54,7 +54,7 @@ def run(B, T, In, H, time_it=False):
         L.check(L.lib().mlvae_debug_set_profile_buffer(L.ptr(prof)), "prof")
         yy.backward(gy); torch.cuda.synchronize()
         L.check(L.lib().mlvae_debug_set_profile_buffer(None), "prof")
-        print("   bwd cycles/step:", dict(zip(["gather+reduce", "gate grads", "mma", "scatter"], [round(v / T) for v in prof.cpu().tolist()[:4]])))
+        print("   bwd cycles/step:", dict(zip(["exchange wait", "reduce", "gate grads + hand-off", "mma completion + scatter", "issuer 0: wait dA", "issuer 0: issue + commit", "issuer 1: wait dA", "issuer 1: issue + commit"], [round(v / T) for v in prof.cpu().tolist()[:8]])))
         lb = ref.bfloat16()
         def rstep():
             xb = x.clone().requires_grad_(True)
