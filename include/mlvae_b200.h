@@ -234,6 +234,46 @@ int mlvae_dense_bwd_prep(const void *d_dy, const void *d_y, void *d_g, float *d_
                          void *d_scratch, void *stream);
 
 /* ------------------------------------------------------------------------- *
+ * TMA-fed tcgen05 GEMM (csrc/gemm.cu) for the time-parallel matrix products of the step -- what torch dispatches
+ * to cuBLAS for nn.LSTM / nn.Linear (modules/decoder.py:14-15,22 input projection x W_ih^T + b, its input / weight
+ * gradients; modules/fc_block.py:9-16 weight gradients and wide forward layers):
+ *     D_i[M, N] (+)= epilogue( A_i B_i ),   i < nprob problems of one shape in one launch, bf16 operands, f32 accumulation
+ *   A: K-major   = row-major (M, K) with row stride lda, or
+ *      MN-major  = row-major (K, M) with row stride lda (i.e. A^T without a transpose pass)
+ *   B: K-major   = row-major (N, K) with row stride ldb (y = x W^T with W as nn.Linear stores it), or
+ *      MN-major  = row-major (K, N) with row stride ldb
+ *   batched reduction (both operands MN-major): D = sum_{b < kbatches} A_b B_b with K rows per batch, batch b at
+ *      element offset b * a_batch_stride / b * b_batch_stride; rows past K of a batch read as zeros.  With row-shifted
+ *      base pointers this is dW_hh = sum_b sum_t dA[b, t+1]^T h[b, t] in one call.
+ *   epilogue: + bias_i[N] (f32, may be NULL), LeakyReLU(0.01) if leaky, the keep mask of mlvae_dropout over the flat
+ *      (M, N) output if drop_p > 0 (needs ldd == N), bf16 or f32 output, accumulate (f32: D += ...), row_perm_H = H > 0:
+ *      output row of GEMM row m is (m % 4) * H + m / 4 (the LSTM kernels' (unit, gate) row order -> torch's (gate, unit)).
+ *   split_k > 1: the reduction is cut in split_k parts whose float32 partials go to ws
+ *      (mlvae_gemm_workspace_bytes) and are added in split order by a second kernel (deterministic); f32 output only.
+ *   bn: N tile (64, 128, 256; 0 = chosen from N).  N, lda, ldb %% 8 == 0; all pointers 16-byte aligned.
+ * ------------------------------------------------------------------------- */
+#define MLVAE_GEMM_MAX_PROBLEMS 4
+typedef struct mlvae_gemm_args {
+    int nprob;
+    const void *A[MLVAE_GEMM_MAX_PROBLEMS];
+    const void *B[MLVAE_GEMM_MAX_PROBLEMS];
+    void *D[MLVAE_GEMM_MAX_PROBLEMS];
+    const float *bias[MLVAE_GEMM_MAX_PROBLEMS];
+    int M, N, K, kbatches;
+    int a_mn_major, b_mn_major;
+    int64_t lda, ldb, a_batch_stride, b_batch_stride, ldd;
+    int out_f32, accumulate, leaky, row_perm_H;
+    int split_k;
+    void *ws;
+    float drop_p;
+    uint64_t drop_seed, drop_offset;
+    const void *drop_offset_add; /* device uint64[1] added to drop_offset, or NULL */
+    int bn;
+} mlvae_gemm_args;
+size_t mlvae_gemm_workspace_bytes(int nprob, int M, int N, int split_k);
+int mlvae_gemm_bf16(const mlvae_gemm_args *args, void *stream);
+
+/* ------------------------------------------------------------------------- *
  * Inter-layer dropout of the stacked LSTM (modules/decoder.py:14-15: nn.LSTM(..., dropout=rnn_dropout),
  * models/test_vanilla_vae/model.yaml dec_rnn_dropout: 0.15), with a reproducible counter-based mask instead
  * of torch's stateful generator.  y = keep ? x / (1 - p) : 0; element i keeps iff the 16-bit lane i % 8
@@ -278,10 +318,15 @@ int mlvae_lstm_bwd(void *d_gates, const float *d_c, const void *d_dy, const void
 /* Parameter plumbing of one bidirectional layer (nn.LSTM's parameters, modules/decoder.py:14-15): masters[8] / grads[8] =
  * {weight_ih, weight_hh, bias_ih, bias_hh} of the forward direction then of the _reverse one, float32 device pointers in
  * torch's (gate, unit) row order.  pack: -> bf16 W_ih (8H x In) with rows in the kernels' (direction, unit, gate) order,
- * bf16 W_hh (2, 4H, H), bf16 bias (8H) = b_ih + b_hh in kernel order.  unpack: float32 gradients dW_ih (8H x In) and
+ * bf16 W_hh (2, 4H, H), FLOAT32 bias (8H) = b_ih + b_hh in kernel order (added by the GEMM epilogue).  unpack (only used
+ * when the weight-gradient GEMMs cannot write torch's row order themselves): float32 gradients dW_ih (8H x In) and
  * dW_hh (4H x H per direction, NULL when T == 1) in kernel row order and db (8H, torch order, both biases) are
  * un-permuted and ACCUMULATED into grads[].  In % 4 == 0, H % 4 == 0, weights 16-byte aligned. */
 int mlvae_lstm_pack_weights(const float *const *masters, int In, int H, void *d_w_ih_p, void *d_w_hh, void *d_bias_p, void *stream);
+/* d_db_part (slices, 2, 4H): the per-slice bias-gradient partials mlvae_lstm_bwd wrote; summed in slice order and ACCUMULATED
+ * into the four float32 bias gradients (bias_ih and bias_hh of a direction receive the same gradient). */
+int mlvae_lstm_bias_grads(const float *d_db_part, int slices, int H, float *d_g_ih_f, float *d_g_hh_f, float *d_g_ih_r, float *d_g_hh_r,
+                          void *stream);
 int mlvae_lstm_unpack_grads(const float *d_dw_ih_p, const float *d_dw_hh_p0, const float *d_dw_hh_p1, const float *d_db, int In, int H,
                             float *const *grads, void *stream);
 

@@ -20,6 +20,15 @@ RECON = {"likelihood": 0, "mse": 1}
 
 _vp, _i, _i64, _u64, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_size_t
 
+class GemmArgs(C.Structure):
+    """mlvae_gemm_args (include/mlvae_b200.h)."""
+    _fields_ = [("nprob", _i), ("A", _vp * 4), ("B", _vp * 4), ("D", _vp * 4), ("bias", _vp * 4),
+                ("M", _i), ("N", _i), ("K", _i), ("kbatches", _i), ("a_mn_major", _i), ("b_mn_major", _i),
+                ("lda", _i64), ("ldb", _i64), ("a_batch_stride", _i64), ("b_batch_stride", _i64), ("ldd", _i64),
+                ("out_f32", _i), ("accumulate", _i), ("leaky", _i), ("row_perm_H", _i), ("split_k", _i), ("ws", _vp),
+                ("drop_p", C.c_float), ("drop_seed", _u64), ("drop_offset", _u64), ("drop_offset_add", _vp), ("bn", _i)]
+
+
 # name -> (restype, argtypes); mirrors include/mlvae_b200.h one to one
 SIGNATURES = {
     "mlvae_abi_version": (_i, []),
@@ -55,9 +64,12 @@ SIGNATURES = {
     "mlvae_dense_bwd_scratch_bytes": (C.c_size_t, [_i]),
     "mlvae_dense_bwd_prep": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i64, C.c_float, _vp, _vp]),
     "mlvae_lstm_pack_weights": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "mlvae_lstm_bias_grads": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "mlvae_lstm_unpack_grads": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "mlvae_pcm_unpack": (_i, [_vp, _i, _vp, _vp, _i, _i64, C.c_float, _vp, _vp]),
     "mlvae_tc05_selftest": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "mlvae_gemm_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "mlvae_gemm_bf16": (_i, [C.POINTER(GemmArgs), _vp]),
     "mlvae_dropout": (_i, [_vp, _vp, _i64, C.c_float, _u64, _u64, _vp, _i, _vp]),
     "mlvae_fbank_fwd": (_i, [_vp, _vp, _vp, _i, _i64, _i64, _i, _vp, _i, _i, _vp, _vp, _vp]),
 }

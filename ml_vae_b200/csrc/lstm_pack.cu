@@ -2,7 +2,8 @@
 // torch ops (cat / cast / gather / add):
 //   pack    float32 masters in torch's layout (weight_ih_l*, weight_hh_l*, bias_ih_l*, bias_hh_l* and their _reverse
 //           twins, modules/decoder.py:14-15)  ->  bf16 W_ih with rows in the kernels' (direction, unit, gate) order,
-//           bf16 W_hh (2, 4H, H), bf16 bias = b_ih + b_hh in kernel order
+//           bf16 W_hh (2, 4H, H), float32 bias = b_ih + b_hh in kernel order (added in the GEMM epilogue in float32)
+//   bias    per-slice bias-gradient partials of the backward recurrence -> ACCUMULATED into b_ih / b_hh gradients
 //   unpack  float32 weight gradients in kernel row order  ->  ACCUMULATED into the eight float32 gradient tensors
 //           in torch's (direction, gate, unit) order (bias gradient added to both b_ih and b_hh)
 #include "common.cuh"
@@ -24,7 +25,7 @@ struct LstmGrads {
 __device__ __forceinline__ int torch_row(int r, int H) { return (r & 3) * H + (r >> 2); }
 
 __global__ void __launch_bounds__(kPackThreads) lstm_pack_kernel(LstmMasters m, int In, int H, bf16 *__restrict__ w_ih_p,
-                                                                 bf16 *__restrict__ w_hh, bf16 *__restrict__ bias_p) {
+                                                                 bf16 *__restrict__ w_hh, float *__restrict__ bias_p) {
     const int H4 = 4 * H;
     const int64_t n_ih = (int64_t)2 * H4 * (In / 4), n_hh = (int64_t)2 * H4 * (H / 4), n_b = 2 * H4;
     for (int64_t i = (int64_t)blockIdx.x * kPackThreads + threadIdx.x; i < n_ih + n_hh + n_b; i += (int64_t)gridDim.x * kPackThreads) {
@@ -47,7 +48,7 @@ __global__ void __launch_bounds__(kPackThreads) lstm_pack_kernel(LstmMasters m, 
                 make_uint2(*reinterpret_cast<const uint32_t *>(&lo), *reinterpret_cast<const uint32_t *>(&hi));
         } else {
             const int k = (int)(i - n_ih - n_hh), d = k / H4, r = k - d * H4, t = torch_row(r, H);
-            bias_p[k] = __float2bfloat16_rn(m.b_ih[d][t] + m.b_hh[d][t]);
+            bias_p[k] = m.b_ih[d][t] + m.b_hh[d][t];
         }
     }
 }
@@ -89,6 +90,18 @@ __global__ void __launch_bounds__(kPackThreads) lstm_unpack_grads_kernel(const f
     }
 }
 
+// db (torch order, (slices, 2, 4H)) summed over the slices in index order and added to the four bias gradients
+__global__ void __launch_bounds__(kPackThreads) lstm_bias_grads_kernel(const float *__restrict__ db_part, int slices, int H, float *__restrict__ g_ih_f,
+                                                                       float *__restrict__ g_hh_f, float *__restrict__ g_ih_r, float *__restrict__ g_hh_r) {
+    const int H4 = 4 * H;
+    for (int k = blockIdx.x * kPackThreads + threadIdx.x; k < 2 * H4; k += gridDim.x * kPackThreads) {
+        float acc = 0.f;
+        for (int s = 0; s < slices; ++s) acc += db_part[(size_t)s * 2 * H4 + k];
+        const int d = k / H4, t = k - d * H4;
+        if (d == 0) { g_ih_f[t] += acc; g_hh_f[t] += acc; } else { g_ih_r[t] += acc; g_hh_r[t] += acc; }
+    }
+}
+
 int grid_for_items(int64_t n) {
     int64_t b = (n + kPackThreads - 1) / kPackThreads;
     const int64_t cap = (int64_t)sm_count() * 8;
@@ -115,7 +128,17 @@ int mlvae_lstm_pack_weights(const float *const *masters, int In, int H, void *d_
                       "lstm_pack_weights: weights must be 16-byte aligned");
     }
     const int64_t n = (int64_t)8 * H * (In / 4) + (int64_t)8 * H * (H / 4) + 8 * H;
-    lstm_pack_kernel<<<grid_for_items(n), kPackThreads, 0, (cudaStream_t)stream>>>(m, In, H, (bf16 *)d_w_ih_p, (bf16 *)d_w_hh, (bf16 *)d_bias_p);
+    lstm_pack_kernel<<<grid_for_items(n), kPackThreads, 0, (cudaStream_t)stream>>>(m, In, H, (bf16 *)d_w_ih_p, (bf16 *)d_w_hh, (float *)d_bias_p);
+    MLVAE_CHECK_CUDA(cudaGetLastError());
+    return MLVAE_OK;
+}
+
+// d_db_part (slices, 2, 4H) float32 (mlvae_lstm_bwd) -> summed over the slices (fixed order) and ACCUMULATED into the four bias
+// gradients (bias_ih / bias_hh get the same gradient: the layer adds them, modules/decoder.py:14-15 via nn.LSTM).
+int mlvae_lstm_bias_grads(const float *d_db_part, int slices, int H, float *d_g_ih_f, float *d_g_hh_f, float *d_g_ih_r, float *d_g_hh_r,
+                          void *stream) {
+    MLVAE_REQUIRE(d_db_part && d_g_ih_f && d_g_hh_f && d_g_ih_r && d_g_hh_r && slices > 0 && H > 0, MLVAE_ERR_INVALID_ARG, "lstm_bias_grads: bad arguments");
+    lstm_bias_grads_kernel<<<grid_for_items(8 * H), kPackThreads, 0, (cudaStream_t)stream>>>(d_db_part, slices, H, d_g_ih_f, d_g_hh_f, d_g_ih_r, d_g_hh_r);
     MLVAE_CHECK_CUDA(cudaGetLastError());
     return MLVAE_OK;
 }

@@ -5,8 +5,8 @@ activation; the ``dropout`` argument is accepted and ignored there).
 
 bf16 activations run every Linear(+LeakyReLU) on the tcgen05 / TMEM kernel ``mlvae_linear_fwd``
 (csrc/gemm_chain.cu): forward and the input gradient (the same kernel against W^T); the weight
-gradient dW = g^T x is a reduction over all B*T rows and stays a library GEMM in round 1, as does the
-whole stack in float32 (tensor cores would break the fp32 1e-5 parity).  ``linear_chain`` is the single
+gradient dW = g^T x, a reduction over all B*T rows, runs on the TMA / tcgen05 GEMM (csrc/gemm.cu, split-K).
+The float32 stack stays on library GEMMs (bf16 tensor cores would break the fp32 1e-5 parity).  ``linear_chain`` is the single
 seam every module goes through.
 """
 from __future__ import annotations
@@ -51,6 +51,22 @@ def _bwd_prep(dy: torch.Tensor, y):
     return (g if y is not None else dy), db
 
 
+def _weight_grad(g: torch.Tensor, x2: torch.Tensor) -> torch.Tensor:
+    """dW = g^T x (float32) on the TMA / tcgen05 GEMM (csrc/gemm.cu): both operands MN-major (no transposes), the reduction over
+    the B*T rows split across the SMs with a deterministic second pass.  Odd shapes fall back to a library GEMM."""
+    M, N = g.shape
+    K = x2.shape[1]
+    if (N % 8 == 0 and K % 8 == 0 and g.stride(1) == 1 and x2.stride(1) == 1 and g.stride(0) % 8 == 0 and x2.stride(0) % 8 == 0
+            and g.data_ptr() % 16 == 0 and x2.data_ptr() % 16 == 0 and g.dtype == torch.bfloat16 and x2.dtype == torch.bfloat16):
+        from .gemm import gemm
+        dw = torch.empty(N, K, dtype=torch.float32, device=g.device)
+        tiles = ((N + 127) // 128) * ((K + 255) // 256)
+        split = max(1, min(32, 128 // tiles, (M + 1023) // 1024))
+        gemm(g, x2, dw, N, K, M, lda=g.stride(0), ldb=x2.stride(0), ldd=K, a_mn=True, b_mn=True, out_f32=True, split_k=split)
+        return dw
+    return torch.mm(g.t(), x2, out_dtype=torch.float32)
+
+
 class _LinearTC(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x2, w, b, leaky):
@@ -76,7 +92,7 @@ class _LinearTC(torch.autograd.Function):
                 dx = _launch(g, wb.t().contiguous(), None, K, False)      # dx = g W  ==  linear(g, W^T)
             else:
                 dx = g @ wb
-        dw = torch.mm(g.t(), x2, out_dtype=torch.float32)       # float32 straight out of the GEMM
+        dw = _weight_grad(g, x2)
         if db is None:
             db = g.sum(0, dtype=torch.float32)
         return dx, dw, db, None

@@ -2,9 +2,9 @@
 
 Replaces, for bf16 activations, the cuDNN path behind ``nn.LSTM(..., bidirectional=True,
 batch_first=True)`` that the reference's Decoder uses (modules/decoder.py:14-15,22).  The big,
-time-parallel GEMMs (input projection, dX, dW_ih, dW_hh) are library GEMMs through torch; the
-sequential part -- T dependent steps per direction -- is ONE cooperative kernel per pass instead
-of 2 x T cuDNN launches.  Gate order and parameter layout are torch's (i, f, g, o).
+time-parallel GEMMs (input projection, dX, dW_ih, dW_hh) run on the TMA / tcgen05 GEMM of
+csrc/gemm.cu; the sequential part -- T dependent steps per direction -- is ONE cooperative kernel
+per pass instead of 2 x T cuDNN launches.  Gate order and parameter layout are torch's (i, f, g, o).
 """
 from __future__ import annotations
 
@@ -87,33 +87,58 @@ def _packable(masters, In: int, H: int) -> bool:
                                               for m in masters)
 
 
+def _gemm_ok(In: int, H: int, x: torch.Tensor) -> bool:
+    """Shapes the TMA GEMM takes: 16-byte aligned rows of every operand."""
+    return In % 8 == 0 and H % 8 == 0 and x.data_ptr() % 16 == 0
+
+
 class _BiLSTMLayer(torch.autograd.Function):
     """One bidirectional layer.  Takes torch's eight per-direction float32 master parameters directly and hands their
-    gradients back in float32, so autograd needs no cat / cast / add nodes (and their kernels) around the layer."""
+    gradients back in float32, so autograd needs no cat / cast / add nodes (and their kernels) around the layer.
+
+    Every matrix product of the layer runs on the TMA / tcgen05 GEMM of csrc/gemm.cu (``gemm.gemm``): the input projection
+    (+ float32 bias in the epilogue), the input gradient (+ the dropout mask of the layer's input, if any, in the epilogue) and
+    the weight gradients, which the GEMM accumulates straight into torch-ordered float32 tensors -- the parameters' own
+    ``.grad`` buffers when ``direct_grads`` -- with dW_hh as ONE batched GEMM over row-shifted views."""
 
     @staticmethod
-    def forward(ctx, x, w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r, training, direct_grads, after_recurrence):
-        """x (B,T,In) bf16 -> y (B,T,2H) bf16."""
+    def forward(ctx, x, w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r, training, direct_grads, after_recurrence,
+                input_dropout):
+        """x (B,T,In) bf16 -> y (B,T,2H) bf16.  ``input_dropout`` = (p, seed, offset, offset_dev) or None: the layer's input is
+        dropout(x) with the counter-based mask of csrc/dropout.cu (the inter-layer dropout of nn.LSTM, decoder.py:14-15)."""
+        from .gemm import gemm
         B, T, In = x.shape
         H = w_hh_f.shape[1]
         bf = torch.bfloat16
+        if input_dropout is not None:
+            p_drop, d_seed, d_off, d_dev = input_dropout
+            xd = torch.empty_like(x)
+            L.check(L.lib().mlvae_dropout(L.ptr(x), L.ptr(xd), x.numel(), float(p_drop), d_seed, d_off, L.ptr(d_dev), L.BF16, L.stream_ptr()),
+                    "mlvae_dropout")
+            x = xd
         x2 = x.reshape(B * T, In)
         masters = (w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r)
         if _packable(masters, In, H):
             # one launch: cast + stack + permute (csrc/lstm_pack.cu)
             w_ih_p = torch.empty(8 * H, In, dtype=bf, device=x.device)       # rows in (dir, unit, gate) order
             w_hh = torch.empty(2, 4 * H, H, dtype=bf, device=x.device)
-            bias_p = torch.empty(8 * H, dtype=bf, device=x.device)
+            bias_p = torch.empty(8 * H, dtype=torch.float32, device=x.device)
             L.check(L.lib().mlvae_lstm_pack_weights(_ptr_array(masters), In, H, L.ptr(w_ih_p), L.ptr(w_hh), L.ptr(bias_p),
                                                     L.stream_ptr()), "mlvae_lstm_pack_weights")
         else:
             perm, _ = _gate_perm(H, x.device)
-            w_ih_p = torch.cat([w_ih_f, w_ih_r], 0).to(bf)[perm]
+            w_ih_p = torch.cat([w_ih_f, w_ih_r], 0).to(bf)[perm].contiguous()
             w_hh = torch.stack([w_hh_f, w_hh_r], 0).to(bf)
-            bias_p = torch.cat([b_ih_f + b_hh_f, b_ih_r + b_hh_r], 0).to(bf)[perm]
+            bias_p = torch.cat([b_ih_f + b_hh_f, b_ih_r + b_hh_r], 0).float()[perm].contiguous()
         ctx.masters = masters if (training and direct_grads) else None
         ctx.after_recurrence = after_recurrence
-        P = torch.addmm(bias_p, x2, w_ih_p.t()).view(B, T, 2, 4 * H)         # library GEMM (time-parallel)
+        ctx.input_dropout = input_dropout
+        ctx.use_gemm = _gemm_ok(In, H, x2)
+        if ctx.use_gemm:
+            P = torch.empty(B, T, 2, 4 * H, dtype=bf, device=x.device)
+            gemm(x2, w_ih_p, P, B * T, 8 * H, In, lda=In, ldb=In, ldd=8 * H, bias=bias_p)
+        else:
+            P = torch.addmm(bias_p.to(bf), x2, w_ih_p.t()).view(B, T, 2, 4 * H)  # odd shapes: library GEMM
         y = torch.empty(B, T, 2 * H, dtype=bf, device=x.device)
         c = torch.empty(B, T, 2 * H, dtype=torch.float32, device=x.device) if training else None
         ev = _probe_start()
@@ -130,6 +155,7 @@ class _BiLSTMLayer(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
+        from .gemm import gemm
         x, w_ih_p, w_hh, gates, c, y = ctx.saved_tensors
         if getattr(ctx, "consumed", False):
             # the backward kernel overwrites the saved gates in place with the pre-activation gradients (raw pointers, so
@@ -139,50 +165,83 @@ class _BiLSTMLayer(torch.autograd.Function):
         ctx.consumed = True
         B, T, In = x.shape
         H = w_hh.shape[2]
+        H4 = 4 * H
+        dev = x.device
         dy = dy.contiguous().to(torch.bfloat16)
         ev = _probe_start()
-        rows = max_rows_per_launch(H, x.device)
-        db_part = torch.empty(sum((min(B, b0 + rows) - b0 + 15) // 16 for b0 in range(0, B, rows)), 8 * H, dtype=torch.float32,
-                              device=x.device)
+        rows = max_rows_per_launch(H, dev)
+        n_slices = sum((min(B, b0 + rows) - b0 + 15) // 16 for b0 in range(0, B, rows))
+        db_part = torch.empty(n_slices, 8 * H, dtype=torch.float32, device=dev)
         part0 = 0
         for b0 in range(0, B, rows):
             b1 = min(B, b0 + rows)
             L.check(L.lib().mlvae_lstm_bwd(L.ptr(gates[b0:b1]), L.ptr(c[b0:b1]), L.ptr(dy[b0:b1]), L.ptr(w_hh), L.ptr(db_part[part0:]),
-                                           b1 - b0, T, H, L.ptr(_get_scratch(b1 - b0, H, x.device)), L.stream_ptr()), "mlvae_lstm_bwd")
+                                           b1 - b0, T, H, L.ptr(_get_scratch(b1 - b0, H, dev)), L.stream_ptr()), "mlvae_lstm_bwd")
             part0 += (b1 - b0 + 15) // 16
         _probe_end("lstm_bwd", ev)
         if ctx.after_recurrence is not None:
             ctx.after_recurrence()                                         # e.g. start the all-reduce of the layers above
         dA = gates                                                         # now pre-activation gradients (B,T,2,H,4)
         dA2 = dA.view(B * T, 8 * H)                                        # columns in (dir, unit, gate) order
-        _, inv = _gate_perm(H, x.device)
         x2 = x.reshape(B * T, In)
-        dx = (dA2 @ w_ih_p).view(B, T, In) if ctx.needs_input_grad[0] else None
-        dw_ih_p = _mm_f32(dA2.t(), x2)                                     # (8H, In) float32, kernel row order
-        db = db_part.sum(0)                                                # bias gradient, reduced inside the kernel (torch order)
-        H4 = 4 * H
+        y2 = y.view(B * T, 2 * H)
         masters = ctx.masters
-        if masters is not None and all(m.grad is not None and m.grad.dtype == torch.float32 and m.grad.is_contiguous()
-                                       and m.grad.data_ptr() % 16 == 0 for m in masters) and In % 4 == 0 and H % 4 == 0:
-            # the owner of the parameters keeps float32 gradient buffers (train_step.FlatArena): un-permute and ACCUMULATE
-            # all eight gradients into them in one launch; autograd gets nothing to add
-            g0 = g1 = None
-            if T > 1:
-                y2 = y.view(B * T, 2 * H)
-                g0 = _mm_f32(dA2[1:, :H4].t(), y2[:-1, :H])
-                g1 = _mm_f32(dA2[:-1, H4:].t(), y2[1:, H:])
-                if B > 1:
-                    g0 -= _mm_f32(dA[1:, 0, 0].t(), y[:-1, T - 1, :H])
-                    g1 -= _mm_f32(dA[:-1, T - 1, 1].t(), y[1:, 0, H:])
-            L.check(L.lib().mlvae_lstm_unpack_grads(L.ptr(dw_ih_p), L.ptr(g0), L.ptr(g1), L.ptr(db), In, H,
-                                                    _ptr_array([m.grad for m in masters]), L.stream_ptr()), "mlvae_lstm_unpack_grads")
-            return (dx,) + (None,) * 11
-        dw_ih = dw_ih_p[inv]                                               # torch row order
+        direct = masters is not None and all(m.grad is not None and m.grad.dtype == torch.float32 and m.grad.is_contiguous()
+                                             and m.grad.data_ptr() % 16 == 0 for m in masters)
+        if not ctx.use_gemm:
+            return _BiLSTMLayer._backward_library(ctx, dA, dA2, x2, y, y2, w_ih_p, db_part, masters if direct else None, B, T, In, H)
+
+        # ---- input gradient: dx = dA W_ih (W_ih row-major (8H, In): MN-major B), the input's dropout mask in the epilogue ----
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(B, T, In, dtype=torch.bfloat16, device=dev)
+            kw = {}
+            if ctx.input_dropout is not None:
+                p_drop, d_seed, d_off, d_dev = ctx.input_dropout
+                kw = dict(drop_p=p_drop, drop_seed=d_seed, drop_offset=d_off, drop_offset_dev=d_dev)
+            gemm(dA2, w_ih_p, dx, B * T, In, 8 * H, lda=8 * H, ldb=In, ldd=In, b_mn=True, **kw)
+        # ---- weight gradients, float32, torch (gate, unit) row order, accumulated where they live ----
+        if direct:
+            g_ih, g_hh = [masters[0].grad, masters[4].grad], [masters[1].grad, masters[5].grad]
+            g_b = [masters[2].grad, masters[3].grad, masters[6].grad, masters[7].grad]
+        else:
+            g_ih = [torch.empty(H4, In, dtype=torch.float32, device=dev) for _ in range(2)]
+            g_hh = [torch.zeros(H4, H, dtype=torch.float32, device=dev) for _ in range(2)]
+            g_b = [torch.zeros(H4, dtype=torch.float32, device=dev) for _ in range(4)]
+        # dW_ih[d] = dA[:, d]^T x: both operands MN-major; few output tiles for a narrow input -> split the B*T reduction
+        tiles = 2 * ((H4 + 127) // 128) * ((In + 255) // 256)
+        split = 1 if tiles >= 96 else max(1, min(8, 128 // tiles))
+        gemm([dA2[:, :H4], dA2[:, H4:]], [x2, x2], g_ih, H4, In, B * T, lda=8 * H, ldb=In, ldd=In, a_mn=True, b_mn=True, out_f32=True,
+             accumulate=direct, row_perm_H=H, split_k=split)
         if T > 1:
-            # dW_hh[d] = sum_{b,t} dA[b,t,d]^T h_prev[b,t,d] with h_prev the previous step IN THAT DIRECTION'S ORDER
-            # (forward: y[b,t-1,:H]; reverse: y[b,t+1,H:]).  On the flattened (B*T) row axis that is one strided GEMM
-            # of rows r against rows r-1 (r+1) -- no copies -- minus the B-1 pairs that straddle two utterances.
-            y2 = y.view(B * T, 2 * H)
+            # dW_hh[d] = sum_b sum_t dA[b,t,d]^T h_prev[b,t,d], h_prev the previous step IN THAT DIRECTION'S ORDER (forward: y[b,t-1,:H];
+            # reverse: y[b,t+1,H:]): a batched reduction over row-shifted views, T-1 rows per utterance (TMA zero-fills past them)
+            tiles = 2 * ((H4 + 127) // 128) * ((H + 255) // 256)
+            split = 1 if tiles >= 96 else max(1, min(4, 128 // tiles))
+            gemm([dA2[1:, :H4], dA2[:, H4:]], [y2[:, :H], y2[1:, H:]], g_hh, H4, H, T - 1, lda=8 * H, ldb=2 * H, ldd=H, a_mn=True, b_mn=True,
+                 kbatches=B, a_batch_stride=T * 8 * H, b_batch_stride=T * 2 * H, out_f32=True, accumulate=direct, row_perm_H=H, split_k=split)
+        L.check(L.lib().mlvae_lstm_bias_grads(L.ptr(db_part), n_slices, H, L.ptr(g_b[0]), L.ptr(g_b[1]), L.ptr(g_b[2]), L.ptr(g_b[3]), L.stream_ptr()),
+                "mlvae_lstm_bias_grads")
+        if direct:
+            return (dx,) + (None,) * 12
+        return dx, g_ih[0], g_hh[0], g_b[0], g_b[1], g_ih[1], g_hh[1], g_b[2], g_b[3], None, None, None, None
+
+    @staticmethod
+    def _backward_library(ctx, dA, dA2, x2, y, y2, w_ih_p, db_part, masters, B, T, In, H):
+        """Input sizes the TMA GEMM does not take (In or H not a multiple of 8): the same products as library GEMMs."""
+        H4 = 4 * H
+        dev = x2.device
+        _, inv = _gate_perm(H, dev)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = (dA2 @ w_ih_p).view(B, T, In)
+            if ctx.input_dropout is not None:
+                p_drop, d_seed, d_off, d_dev = ctx.input_dropout
+                L.check(L.lib().mlvae_dropout(L.ptr(dx), L.ptr(dx), dx.numel(), float(p_drop), d_seed, d_off, L.ptr(d_dev), L.BF16, L.stream_ptr()),
+                        "mlvae_dropout")
+        dw_ih = _mm_f32(dA2.t(), x2)[inv]
+        db = db_part.sum(0)
+        if T > 1:
             g0 = _mm_f32(dA2[1:, :H4].t(), y2[:-1, :H])
             g1 = _mm_f32(dA2[:-1, H4:].t(), y2[1:, H:])
             if B > 1:
@@ -190,17 +249,23 @@ class _BiLSTMLayer(torch.autograd.Function):
                 g1 -= _mm_f32(dA[:-1, T - 1, 1].t(), y[1:, 0, H:])
             dw_hh_f, dw_hh_r = g0[inv[:H4]], g1[inv[:H4]]
         else:
-            dw_hh_f = torch.zeros(H4, H, dtype=torch.float32, device=x.device)
+            dw_hh_f = torch.zeros(H4, H, dtype=torch.float32, device=dev)
             dw_hh_r = torch.zeros_like(dw_hh_f)
-        return dx, dw_ih[:H4], dw_hh_f, db[:H4], db[:H4], dw_ih[H4:], dw_hh_r, db[H4:], db[H4:], None, None, None
+        grads = [dw_ih[:H4], dw_hh_f, db[:H4], db[:H4], dw_ih[H4:], dw_hh_r, db[H4:], db[H4:]]
+        if masters is not None:
+            for m, g in zip(masters, grads):
+                m.grad.add_(g)
+            return (dx,) + (None,) * 12
+        return (dx, *grads, None, None, None, None)
 
 
 def bilstm_layer(x, w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r, training: bool, direct_grads: bool = False,
-                 after_recurrence=None):
+                 after_recurrence=None, input_dropout=None):
     """One bidirectional layer with torch's per-direction parameters (float32 masters; cast inside the layer).
     ``direct_grads``: accumulate the parameter gradients straight into the parameters' existing float32 ``.grad``
     buffers (valid under ``loss.backward()``; the training step that owns a flat gradient bucket turns it on).
     ``after_recurrence``: callable run in backward right after the recurrence kernel is enqueued, before the layer's
-    weight-gradient GEMMs."""
+    weight-gradient GEMMs.  ``input_dropout`` = (p, seed, offset, offset_dev): the layer consumes dropout(x) (counter-based
+    mask, csrc/dropout.cu); the mask of the backward pass is applied inside the input-gradient GEMM."""
     return _BiLSTMLayer.apply(x.contiguous(), w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r, training,
-                              direct_grads, after_recurrence)
+                              direct_grads, after_recurrence, input_dropout)

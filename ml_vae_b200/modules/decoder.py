@@ -66,9 +66,13 @@ class Decoder(nn.Module):
                 # train_step.py (data parallel): once the backward recurrence of the layer BELOW the top one is enqueued, the
                 # gradients of the top layer and of the heads are final -> their all-reduce overlaps this layer's GEMMs
                 hook = self.top_layer_grad_hook if (layer + 2 == self.num_layers and need_grad) else None
-                x = lstm.bilstm_layer(x, *ps, training=need_grad, direct_grads=self.direct_param_grads, after_recurrence=hook)
-                if self.rnn_dropout > 0 and self.training and layer + 1 < self.num_layers:
-                    x = ops.dropout(x, self.rnn_dropout, self.dropout_seed, self._dropout_offset(layer), self.dropout_offset_dev)
+                # nn.LSTM's inter-layer dropout (decoder.py:14-15) acts on the INPUT of every layer but the first: handed to the
+                # layer, which applies the counter-based mask going in and folds it into its input-gradient GEMM coming back
+                drop = None
+                if self.rnn_dropout > 0 and self.training and layer > 0:
+                    drop = (self.rnn_dropout, self.dropout_seed, self._dropout_offset(layer - 1), self.dropout_offset_dev)
+                x = lstm.bilstm_layer(x, *ps, training=need_grad, direct_grads=self.direct_param_grads, after_recurrence=hook,
+                                      input_dropout=drop)
             if self.rnn_dropout > 0 and self.training:
                 self.dropout_calls += 1
             return x
