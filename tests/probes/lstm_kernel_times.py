@@ -49,8 +49,9 @@ def timed(fn, make, n=5):
 
 G0 = None
 base = None
-for delay in [int(v) for v in (sys.argv[1:] or ["0", "0"])]:
-    if lib.mlvae_debug_set_option(3, delay) != 0 or lib.mlvae_debug_set_option(4, delay) != 0:
+for delay in (sys.argv[1:] or ["600:0", "600:0"]):          # "fwd:bwd" poll delays in cycles (or one number for both)
+    df, db_ = (delay.split(":") + [delay])[:2]
+    if lib.mlvae_debug_set_option(3, int(df)) != 0 or lib.mlvae_debug_set_option(4, int(db_)) != 0:
         print("(library has no poll-delay knob)")
     P = P0.clone(); fwd(P); torch.cuda.synchronize()
     err = float((Y.float() - ref).abs().max() / ref.abs().max())
