@@ -231,7 +231,23 @@ int mlvae_tc05_selftest(const void *d_a, const void *d_b, float *d_d, int N, int
  * zeroed ONCE by the caller (self-resetting).  Deterministic. */
 size_t mlvae_dense_bwd_scratch_bytes(int N);
 int mlvae_dense_bwd_prep(const void *d_dy, const void *d_y, void *d_g, float *d_db, int64_t M, int N, int64_t ld, float slope,
-                         void *d_scratch, void *stream);
+                         void *d_scratch, int accumulate /* db += instead of db = */, void *stream);
+
+/* ------------------------------------------------------------------------- *
+ * check_gradients + optimizer.step + zero_grad of MDModel.fit_batch (models/md_model.py:82-87) for torch.optim.Adam
+ * (models/test_vanilla_vae/model.yaml:45-47) over ONE flat float32 parameter arena, two launches:
+ *   g *= grad_scale (1 / world_size after the all-reduce);  g *= min(1, max_grad_norm / (||g||_2 + 1e-6))   [clip_grad_norm_]
+ *   step += 1;  m += (g - m)(1 - beta1);  v = beta2 v + (1 - beta2) g g;
+ *   p -= lr / (1 - beta1^step) * m / (sqrt(v) / sqrt(1 - beta2^step) + eps)                                 [torch Adam]
+ *   g = 0;  p_bf16 = bf16(p)   (d_params_bf16 may be NULL)
+ * A non-finite *d_loss (device float, may be NULL) skips the update like check_gradients does (the gradients are still zeroed),
+ * step unchanged.
+ * d_state: mlvae_adam_state_bytes() bytes, zeroed once by the caller ({step, last norm, last clip coefficient, partials}).
+ * max_grad_norm <= 0 disables clipping.  Deterministic.  All buffers 16-byte aligned.
+ * ------------------------------------------------------------------------- */
+size_t mlvae_adam_state_bytes(void);
+int mlvae_adam_clip_step(float *d_params, float *d_grads, float *d_exp_avg, float *d_exp_avg_sq, void *d_params_bf16, int64_t n, float grad_scale,
+                         float lr, float beta1, float beta2, float eps, float max_grad_norm, void *d_state, const float *d_loss, void *stream);
 
 /* ------------------------------------------------------------------------- *
  * TMA-fed tcgen05 GEMM (csrc/gemm.cu) for the time-parallel matrix products of the step -- what torch dispatches

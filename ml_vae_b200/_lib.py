@@ -62,7 +62,9 @@ SIGNATURES = {
     "mlvae_global_norm": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp]),
     "mlvae_linear_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "mlvae_dense_bwd_scratch_bytes": (C.c_size_t, [_i]),
-    "mlvae_dense_bwd_prep": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i64, C.c_float, _vp, _vp]),
+    "mlvae_dense_bwd_prep": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i64, C.c_float, _vp, _i, _vp]),
+    "mlvae_adam_state_bytes": (_sz, []),
+    "mlvae_adam_clip_step": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _vp, _vp, _vp]),
     "mlvae_lstm_pack_weights": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp]),
     "mlvae_lstm_bias_grads": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "mlvae_lstm_unpack_grads": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),

@@ -24,7 +24,7 @@ struct DbScratch {
 
 __global__ void __launch_bounds__(kDbThreads) dense_bwd_prep_kernel(const bf16 *__restrict__ dy, const bf16 *__restrict__ y,
                                                                     bf16 *__restrict__ g, float *__restrict__ db, int64_t M, int N,
-                                                                    int64_t ld, float slope, DbScratch *scratch) {
+                                                                    int64_t ld, float slope, DbScratch *scratch, int accumulate) {
     extern __shared__ float s_acc[];                     // [RP][N]
     __shared__ bool s_last;
     const int VC = N >> 3;                               // 16-byte vectors per row
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(kDbThreads) dense_bwd_prep_kernel(const bf16 *
         if (tid < N - c0 && tid < kDbThreads) {
             float t = 0.f;
             for (int q = 0; q < P; ++q) t += s_acc[q * N + tid];
-            db[c0 + tid] = t;
+            db[c0 + tid] = accumulate ? db[c0 + tid] + t : t;
         }
         __syncthreads();
     }
@@ -127,7 +127,7 @@ extern "C" {
 size_t mlvae_dense_bwd_scratch_bytes(int N) { return N > 0 ? sizeof(DbScratch) + (size_t)kDbMaxGrid * N * sizeof(float) : 0; }
 
 int mlvae_dense_bwd_prep(const void *d_dy, const void *d_y, void *d_g, float *d_db, int64_t M, int N, int64_t ld, float slope,
-                         void *d_scratch, void *stream) {
+                         void *d_scratch, int accumulate, void *stream) {
     MLVAE_REQUIRE(d_dy && d_db && d_scratch, MLVAE_ERR_INVALID_ARG, "dense_bwd_prep: missing buffers");
     MLVAE_REQUIRE((d_y == nullptr) == (d_g == nullptr), MLVAE_ERR_INVALID_ARG, "dense_bwd_prep: y and g go together");
     MLVAE_REQUIRE(M > 0 && N > 0 && N % 8 == 0 && N <= 2048 && ld >= N && ld % 8 == 0, MLVAE_ERR_UNSUPPORTED,
@@ -139,7 +139,7 @@ int mlvae_dense_bwd_prep(const void *d_dy, const void *d_y, void *d_g, float *d_
     const int grid = (int)(blocks < 1 ? 1 : blocks < kDbMaxGrid ? blocks : kDbMaxGrid);
     const size_t smem = (size_t)RP * N * sizeof(float);
     dense_bwd_prep_kernel<<<grid, kDbThreads, smem, (cudaStream_t)stream>>>((const bf16 *)d_dy, (const bf16 *)d_y, (bf16 *)d_g, d_db, M,
-                                                                             N, ld, slope, (DbScratch *)d_scratch);
+                                                                             N, ld, slope, (DbScratch *)d_scratch, accumulate);
     MLVAE_CHECK_CUDA(cudaGetLastError());
     return MLVAE_OK;
 }

@@ -35,8 +35,9 @@ def _launch(x2, w_bf16, bias_f32, n_out, leaky):
 _db_scratch = {}
 
 
-def _bwd_prep(dy: torch.Tensor, y):
-    """g = dy * leaky'(y) (y given) and db = column sums of g, one kernel (csrc/dense_bwd.cu)."""
+def _bwd_prep(dy: torch.Tensor, y, accumulate_into=None):
+    """g = dy * leaky'(y) (y given) and db = column sums of g, one kernel (csrc/dense_bwd.cu).  ``accumulate_into``: a float32
+    (N,) tensor that receives db += ... instead of a fresh one."""
     M, N = dy.shape
     key = (dy.device, torch.cuda.current_stream(dy.device).cuda_stream)
     need = L.lib().mlvae_dense_bwd_scratch_bytes(N)
@@ -45,9 +46,9 @@ def _bwd_prep(dy: torch.Tensor, y):
         buf = torch.zeros(max(need, L.lib().mlvae_dense_bwd_scratch_bytes(256)), dtype=torch.uint8, device=dy.device)
         _db_scratch[key] = buf
     g = torch.empty_like(dy) if y is not None else None
-    db = torch.empty(N, dtype=torch.float32, device=dy.device)
-    L.check(L.lib().mlvae_dense_bwd_prep(L.ptr(dy), L.ptr(y), L.ptr(g), L.ptr(db), M, N, N, LEAKY_SLOPE, L.ptr(buf), L.stream_ptr()),
-            "mlvae_dense_bwd_prep")
+    db = accumulate_into if accumulate_into is not None else torch.empty(N, dtype=torch.float32, device=dy.device)
+    L.check(L.lib().mlvae_dense_bwd_prep(L.ptr(dy), L.ptr(y), L.ptr(g), L.ptr(db), M, N, N, LEAKY_SLOPE, L.ptr(buf), int(accumulate_into is not None),
+                                         L.stream_ptr()), "mlvae_dense_bwd_prep")
     return (g if y is not None else dy), db
 
 
@@ -96,6 +97,65 @@ class _LinearTC(torch.autograd.Function):
         if db is None:
             db = g.sum(0, dtype=torch.float32)
         return dx, dw, db, None
+
+
+class _LinearDirect(torch.autograd.Function):
+    """Linear(+LeakyReLU) over ARENA views (train_step.FlatArena.linear_views): the bf16 shadow weight and float32 bias are read
+    as they are (no cast / cat / transpose kernels), and the backward pass ACCUMULATES dW and db straight into the gradient
+    bucket (GEMM epilogue / bias kernel), so autograd sees one differentiable input and adds nothing."""
+
+    @staticmethod
+    def forward(ctx, x2, w16, b32, gw, gb, leaky, anchor):
+        # `anchor` is the float32 master parameter: only there so that autograd records this node even when x itself does not
+        # require a gradient (first layer of the encoder); its gradient is accumulated in place, not returned
+        N, K = w16.shape
+        if N <= 256:
+            y = _launch(x2, w16, b32, N, leaky)                  # skinny output: the one-pass streaming kernel (csrc/gemm_chain.cu)
+        else:
+            from .gemm import gemm                              # wide output: the tiled TMA GEMM with the same epilogue
+            y = torch.empty(x2.shape[0], N, dtype=torch.bfloat16, device=x2.device)
+            gemm(x2, w16, y, x2.shape[0], N, K, lda=x2.stride(0), ldb=K, ldd=N, bias=b32, leaky=leaky)
+        ctx.save_for_backward(x2, y if leaky else None)
+        ctx.w16, ctx.gw, ctx.gb, ctx.leaky = w16, gw, gb, leaky
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        from .gemm import gemm
+        x2, y = ctx.saved_tensors
+        w16, gw, gb = ctx.w16, ctx.gw, ctx.gb
+        N, K = w16.shape
+        M = x2.shape[0]
+        g = dy if dy.is_contiguous() else dy.contiguous()
+        g, _ = _bwd_prep(g, y if ctx.leaky else None, accumulate_into=gb)          # g = dy * act'(y), db accumulated in place
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(M, K, dtype=torch.bfloat16, device=g.device)
+            gemm(g, w16, dx, M, K, N, lda=N, ldb=K, ldd=K, b_mn=True)                # dx = g W  (W row-major (N, K): MN-major B)
+        tiles = ((N + 127) // 128) * ((K + 255) // 256)
+        split = max(1, min(32, 128 // tiles, (M + 1023) // 1024))
+        gemm(g, x2, gw, N, K, M, lda=N, ldb=x2.stride(0), ldd=K, a_mn=True, b_mn=True, out_f32=True, accumulate=True, split_k=split)
+        return dx, None, None, None, None, None, None
+
+
+def linear_direct(x: torch.Tensor, views, leaky: bool = False) -> torch.Tensor:
+    """x (..., K) bf16 -> act(x W^T + b) with ``views`` = (w_bf16, bias_f32, grad_w, grad_b, master parameter) from
+    FlatArena.linear_views."""
+    L.require_cuda(x)
+    w16, b32, gw, gb, anchor = views
+    lead = x.shape[:-1]
+    x2 = x.reshape(-1, x.shape[-1])
+    if x2.stride(1) != 1 or x2.stride(0) % 8 or x2.data_ptr() % 16:
+        x2 = x2.contiguous()
+    y = _LinearDirect.apply(x2, w16, b32, gw, gb, leaky, anchor)
+    return y.reshape(*lead, w16.shape[0])
+
+
+def direct_chain(x: torch.Tensor, views_list, end_activation: bool = False) -> torch.Tensor:
+    n = len(views_list)
+    for i, v in enumerate(views_list):
+        x = linear_direct(x, v, leaky=(i + 1 < n or end_activation))
+    return x
 
 
 def linear(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, leaky: bool = False) -> torch.Tensor:

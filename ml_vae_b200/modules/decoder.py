@@ -16,7 +16,7 @@ import torch
 from torch import nn
 
 from .. import lstm, ops
-from ..dense import linear, linear_chain
+from ..dense import direct_chain, linear, linear_chain, linear_direct
 from ._params import attach, torch_default_linear, torch_default_lstm
 
 
@@ -48,6 +48,25 @@ class Decoder(nn.Module):
                 w, b = torch_default_linear(self.fc_sizes[i], self.fc_sizes[i + 1])
                 attach(self, f"{head}.blocks.{2 * i}.weight", w)
                 attach(self, f"{head}.blocks.{2 * i}.bias", b)
+
+    # -- flat-arena binding (train_step.FlatArena) -------------------------------------------------------------
+    def adjacent_param_groups(self):
+        """Parameters the arena should lay out back to back: the first layers of the two heads run as ONE stacked GEMM."""
+        (wm, bm), (wv, bv) = self._head("mean_fc"), self._head("log_var_fc")
+        if len(wm) > 1 and wm[0].shape == wv[0].shape:
+            return [[wm[0], wv[0]], [bm[0], bv[0]]]
+        return []
+
+    def bind_arena(self, arena):
+        """Use the arena's bf16 shadow weights directly and accumulate the dense gradients in its bucket (bf16 path only)."""
+        (wm, bm), (wv, bv) = self._head("mean_fc"), self._head("log_var_fc")
+        self._direct = None
+        if len(wm) > 1 and wm[0].shape == wv[0].shape:
+            head0 = arena.linear_views([wm[0], wv[0]], [bm[0], bv[0]])
+            mean = [arena.linear_views([w], [b]) for w, b in zip(wm[1:], bm[1:])]
+            logv = [arena.linear_views([w], [b]) for w, b in zip(wv[1:], bv[1:])]
+            if head0 is not None and all(v is not None for v in mean + logv):
+                self._direct = (head0, mean, logv)
 
     def _head(self, name):
         blocks = getattr(self, name).blocks._modules
@@ -103,7 +122,14 @@ class Decoder(nn.Module):
             raise ValueError(f"Invalid loss type: {self.loss_type}")
         rnn_out = self.run_rnn(sampled_h)
         (wm, bm), (wv, bv) = self._head("mean_fc"), self._head("log_var_fc")
-        if len(wm) > 1 and wm[0].shape == wv[0].shape:
+        direct = getattr(self, "_direct", None)
+        if direct is not None and rnn_out.dtype == torch.bfloat16:
+            head0, mviews, vviews = direct
+            n0 = wm[0].shape[0]
+            h0 = linear_direct(rnn_out, head0, leaky=True)
+            mean = direct_chain(h0[..., :n0], mviews)
+            log_var = direct_chain(h0[..., n0:], vviews)
+        elif len(wm) > 1 and wm[0].shape == wv[0].shape:
             # both heads read the (B, T, 2H) LSTM output: their first layers run as ONE GEMM against the stacked
             # weight, so the widest activation of the model is read once (decoder.py:24-25 reads it twice)
             n0 = wm[0].shape[0]

@@ -19,7 +19,7 @@ import torch
 from torch import nn
 
 from .. import ops
-from ..dense import LEAKY_SLOPE, linear_chain
+from ..dense import LEAKY_SLOPE, direct_chain, linear_chain, linear_direct
 from ._params import attach, torch_default_linear
 
 _DEFAULT_SEED = 123456      # run.yaml:2
@@ -61,8 +61,25 @@ class VanillaVAE(nn.Module):
         n = len(self.fc_sizes) - 1
         return [blocks[str(2 * i)].weight for i in range(n)], [blocks[str(2 * i)].bias for i in range(n)]
 
+    # -- flat-arena binding (train_step.FlatArena) -------------------------------------------------------------
+    def adjacent_param_groups(self):
+        return [[self.mean_fc.weight, self.log_var_fc.weight], [self.mean_fc.bias, self.log_var_fc.bias]]
+
+    def bind_arena(self, arena):
+        ws, bs = self._trunk()
+        trunk = [arena.linear_views([w], [b]) for w, b in zip(ws, bs)]
+        heads = arena.linear_views([self.mean_fc.weight, self.log_var_fc.weight], [self.mean_fc.bias, self.log_var_fc.bias])
+        self._direct = (trunk, heads) if heads is not None and all(v is not None for v in trunk) else None
+
     def project(self, feats):
         """feats (B, T, C) -> mean, log_var (B, T, L).  vanilla_vae.py:22-24."""
+        direct = getattr(self, "_direct", None)
+        if direct is not None and feats.dtype == torch.bfloat16:
+            trunk, heads = direct
+            h = direct_chain(feats, trunk, end_activation=True)
+            ml = linear_direct(h, heads)
+            mean, log_var = ml[..., : self.latent_size], ml[..., self.latent_size:]
+            return mean.contiguous(), log_var.contiguous()
         ws, bs = self._trunk()
         h = linear_chain(feats, ws, bs, end_activation=True)
         # both heads read h once: one GEMM against the stacked (2L, H) weight

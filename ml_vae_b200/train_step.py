@@ -21,6 +21,7 @@ from __future__ import annotations
 import torch
 from torch import nn
 
+from . import _lib as L
 from .parallel import all_reduce_mean_, broadcast_
 
 KLD_N_SAMPLES = 2249          # md_model.py:199
@@ -37,8 +38,14 @@ def loss_weight(hparams: dict, loss_key: str) -> float:
 
 
 class FlatArena:
-    """Re-homes every parameter of ``modules`` into one contiguous float32 buffer (and its
-    gradient into one contiguous bucket) without changing names or values."""
+    """Re-homes every parameter of ``modules`` into one contiguous float32 buffer (and its gradient into one contiguous
+    bucket) without changing names or values, plus what the fused optimiser / tensor-core kernels want next to it:
+    Adam's two moment buffers, and a bf16 SHADOW of the parameters that the optimiser kernel refreshes after every update
+    (``flat_bf16``; no per-layer cast kernels in the step).  Parameters a module wants stacked into one GEMM operand
+    (``module.adjacent_param_groups()``) are laid out back to back; every parameter starts at a multiple of 8 elements
+    (16-byte aligned bf16 / float32 rows for TMA and vector loads)."""
+
+    ALIGN = 8
 
     def __init__(self, modules):
         params, seen = [], set()
@@ -47,39 +54,91 @@ class FlatArena:
                 if id(p) not in seen:
                     seen.add(id(p))
                     params.append(p)
-        self.params = params
-        n = sum(p.numel() for p in params)
-        dev = params[0].device
-        self.flat = torch.empty(n, dtype=torch.float32, device=dev)
+        # members of an adjacency group follow the group's first member
+        follow = {}
+        for m in modules:
+            for grp in getattr(m, "adjacent_param_groups", lambda: [])():
+                for q in grp[1:]:
+                    follow[id(q)] = grp[0]
+        ordered, placed = [], set()
+        groups = {}
+        for m in modules:
+            for grp in getattr(m, "adjacent_param_groups", lambda: [])():
+                groups[id(grp[0])] = grp
+        for p in params:
+            if id(p) in placed or id(p) in follow:
+                continue
+            for q in groups.get(id(p), [p]):
+                ordered.append(q)
+                placed.add(id(q))
+        self.params = ordered
+        self.offsets, off = {}, 0
+        for p in ordered:
+            off = -(-off // self.ALIGN) * self.ALIGN
+            self.offsets[id(p)] = off
+            off += p.numel()
+        n = -(-off // self.ALIGN) * self.ALIGN
+        dev = ordered[0].device
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
         self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
-        off = 0
+        self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.flat_bf16 = torch.zeros(n, dtype=torch.bfloat16, device=dev)
         with torch.no_grad():
-            for p in params:
-                k = p.numel()
-                self.flat[off:off + k].copy_(p.reshape(-1))
-                p.data = self.flat[off:off + k].view(p.shape)
-                p.grad = self.grad[off:off + k].view(p.shape)
-                off += k
-        self.master = nn.Parameter(self.flat, requires_grad=True)   # what the optimiser sees
+            for p in ordered:
+                o, k = self.offsets[id(p)], p.numel()
+                self.flat[o:o + k].copy_(p.reshape(-1))
+                p.data = self.flat[o:o + k].view(p.shape)
+                p.grad = self.grad[o:o + k].view(p.shape)
+            self.flat_bf16.copy_(self.flat)
+        self.master = nn.Parameter(self.flat, requires_grad=True)   # what a torch optimiser would see
         self.master.grad = self.grad
 
     def zero_grad(self):
         self.grad.zero_()
+
+    def refresh_bf16(self):
+        """Re-derive the bf16 shadow from the float32 masters (after load_state_dict / a foreign optimiser step)."""
+        self.flat_bf16.copy_(self.flat)
 
     def all_reduce_mean(self, world_size: int, group=None, lo: int = 0, hi: int = None):
         all_reduce_mean_(self.grad[lo:hi], world_size, group)
 
     def offset_of(self, param) -> int:
         """Element offset of ``param`` inside the flat buffers."""
-        off = 0
-        for p in self.params:
-            if p is param:
-                return off
-            off += p.numel()
-        raise KeyError("parameter is not in this arena")
+        try:
+            return self.offsets[id(param)]
+        except KeyError:
+            raise KeyError("parameter is not in this arena") from None
+
+    def linear_views(self, weights, biases):
+        """(w_bf16 (N, K), bias_f32 (N), grad_w (N, K), grad_b (N), first master weight) over the arena for one Linear, or for several Linears with
+        the same K whose weights (and biases) sit back to back (then N = sum N_i: one stacked GEMM operand).  None if the
+        layout does not allow it (shapes not multiples of 8, members not adjacent)."""
+        K = weights[0].shape[1]
+        N = sum(w.shape[0] for w in weights)
+        if K % 8 or N % 8 or any(w.shape[1] != K or w.shape[0] % 8 for w in weights):
+            return None
+        def run(ps):
+            o0 = self.offset_of(ps[0])
+            o = o0
+            for p in ps:
+                if self.offset_of(p) != o:
+                    return None
+                o += p.numel()
+            return o0
+        try:
+            ow, ob = run(weights), run(biases)
+        except KeyError:
+            return None
+        if ow is None or ob is None:
+            return None
+        return (self.flat_bf16[ow:ow + N * K].view(N, K), self.flat[ob:ob + N], self.grad[ow:ow + N * K].view(N, K), self.grad[ob:ob + N],
+                weights[0])
 
     def broadcast(self, src: int = 0, group=None):
         broadcast_(self.flat, src, group)
+        self.refresh_bf16()
 
 
 class TrainStep:
@@ -92,8 +151,15 @@ class TrainStep:
         self.world_size = world_size
         self.max_grad_norm = max_grad_norm
         self.arena = FlatArena([encoder, decoder])
-        # optimizer: !name:torch.optim.Adam {lr: 0.001}  (models/test_vanilla_vae/model.yaml:45-47)
-        self.opt = torch.optim.Adam([self.arena.master], lr=lr, fused=True, capturable=True)
+        # optimizer: !name:torch.optim.Adam {lr: 0.001}  (models/test_vanilla_vae/model.yaml:45-47): torch's defaults, run by the
+        # fused clip + Adam + zero_grad + bf16-shadow kernel pair of csrc/optim.cu over the flat arena
+        self.lr, self.betas, self.eps = lr, (0.9, 0.999), 1e-8
+        self.adam_state = torch.zeros(L.lib().mlvae_adam_state_bytes() // 4, dtype=torch.float32, device=self.arena.flat.device)
+        if world_size > 1:
+            self.arena.broadcast(0)                            # every rank starts from rank 0's weights (what DDP does at wrap time)
+        for m in (encoder, decoder):
+            if compute_dtype == torch.bfloat16 and hasattr(m, "bind_arena"):
+                m.bind_arena(self.arena)                       # bf16 shadow weights + gradients accumulated in place
         self.w_kld = loss_weight(self.hparams, "kld_loss")
         self.w_rec = loss_weight(self.hparams, "recon_loss")
         self.epoch = 0
@@ -102,7 +168,6 @@ class TrainStep:
         self.decoder.materialize_loss = False
         if hasattr(self.decoder, "direct_param_grads"):
             self.decoder.direct_param_grads = True         # parameter gradients of the LSTM land in the flat bucket directly
-        self.found_inf = torch.zeros((), dtype=torch.float32, device=self.arena.flat.device)
         self.last = {}
         # device-resident step counter = Philox offset of the reparameterisation noise: a captured CUDA graph then
         # draws fresh eps on every replay
@@ -131,7 +196,8 @@ class TrainStep:
         cur = torch.cuda.current_stream()
         self._ar_stream.wait_stream(cur)                      # the tail's gradients were accumulated by earlier backward nodes
         with torch.cuda.stream(self._ar_stream):
-            self.arena.all_reduce_mean(self.world_size, lo=self._split)
+            import torch.distributed as dist
+            dist.all_reduce(self.arena.grad[self._split:], op=dist.ReduceOp.SUM)
         self._early_done = True
         return None
 
@@ -151,17 +217,20 @@ class TrainStep:
         loss, kld, rec = self.losses(feats, rel)
         self._early_done = False
         loss.backward()
-        if self._early_done:
-            self.arena.all_reduce_mean(self.world_size, hi=self._split)
-            torch.cuda.current_stream().wait_stream(self._ar_stream)
-        else:
-            self.arena.all_reduce_mean(self.world_size)
-        # check_gradients [SB-recall]: non-finite loss -> skip the update; clip the global norm
-        torch.nn.utils.clip_grad_norm_([self.arena.master], self.max_grad_norm, foreach=True)
-        self.found_inf.copy_((~torch.isfinite(loss.detach())).float())
-        self.opt.grad_scale, self.opt.found_inf = None, self.found_inf
-        self.opt.step()
-        self.arena.zero_grad()
+        # gradient SUM over the ranks (the 1 / world_size of the mean is applied inside the optimiser kernel)
+        if self.world_size > 1:
+            import torch.distributed as dist
+            if self._early_done:
+                dist.all_reduce(self.arena.grad[:self._split], op=dist.ReduceOp.SUM)
+                torch.cuda.current_stream().wait_stream(self._ar_stream)
+            else:
+                dist.all_reduce(self.arena.grad, op=dist.ReduceOp.SUM)
+        # check_gradients [SB-recall] (non-finite loss -> skip the update; clip the global norm), Adam, zero_grad, bf16 shadow
+        lossf = loss.detach().float().reshape(1)
+        a = self.arena
+        L.check(L.lib().mlvae_adam_clip_step(L.ptr(a.flat), L.ptr(a.grad), L.ptr(a.exp_avg), L.ptr(a.exp_avg_sq), L.ptr(a.flat_bf16), a.flat.numel(),
+                                             1.0 / self.world_size, self.lr, self.betas[0], self.betas[1], self.eps, float(self.max_grad_norm or 0.0),
+                                             L.ptr(self.adam_state), L.ptr(lossf), L.stream_ptr()), "mlvae_adam_clip_step", kernels=2)
         self.step_counter += 1
         self.last = {"loss": loss.detach(), "kld_loss": kld.detach(), "recon_loss": rec.detach()}
         return self.last["loss"]

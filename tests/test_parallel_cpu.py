@@ -42,7 +42,11 @@ def _worker(rank, world, port, out):
     loss.backward()                                 # accumulates straight into the flat bucket
     arena.all_reduce_mean(world)
     if rank == 0:
-        torch.save({"grad": arena.grad.clone(), "flat": arena.flat.clone(), "names": [tuple(p.shape) for p in arena.params]}, out)
+        torch.save({"grad": torch.cat([p.grad.reshape(-1) for p in model.parameters()]),       # the parameters' views of the bucket
+                    "flat": torch.cat([p.detach().reshape(-1) for p in model.parameters()]),
+                    "in_bucket": all(arena.grad.data_ptr() <= p.grad.data_ptr() < arena.grad.data_ptr() + arena.grad.numel() * 4
+                                     for p in model.parameters()),
+                    "bucket_sum": float(arena.grad.double().sum())}, out)
     dist.destroy_process_group()
 
 
@@ -58,6 +62,7 @@ def test_flat_bucket_all_reduce_equals_full_batch_gradient(tmp_path):
     ref = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
     assert torch.allclose(got["grad"], ref, atol=1e-6)
     assert torch.equal(got["flat"], torch.cat([p.detach().reshape(-1) for p in model.parameters()]))
+    assert got["in_bucket"] and abs(got["bucket_sum"] - float(ref.double().sum())) < 1e-5      # alignment gaps of the bucket stay zero
 
 
 def test_flat_arena_keeps_names_values_and_views():
@@ -69,7 +74,20 @@ def test_flat_arena_keeps_names_values_and_views():
     arena = FlatArena([enc, dec])
     after = dict(list(enc.state_dict().items()) + list(dec.state_dict().items()))
     assert list(before) == list(after) and all(torch.equal(before[k], after[k]) for k in before)
-    assert arena.flat.numel() == sum(v.numel() for v in before.values())
+    total = sum(v.numel() for v in before.values())
+    assert total <= arena.flat.numel() < total + 8 * len(before)          # every parameter starts 16-byte aligned (bf16 shadow rows)
+    assert all(arena.offset_of(p) % 8 == 0 for p in arena.params)
+    assert torch.equal(arena.flat_bf16.float(), arena.flat.bfloat16().float())
+    # the heads that run as one stacked GEMM sit back to back: their stacked views are plain slices of the arena
+    views = arena.linear_views([enc.mean_fc.weight, enc.log_var_fc.weight], [enc.mean_fc.bias, enc.log_var_fc.bias])
+    assert views is None                                                      # latent 4: rows not a multiple of 8 -> generic path
+    enc8, dec8 = VanillaVAE([16, 8, 8], 8), Decoder(8, 8, 1, 0.0, [16, 8, 8, 16])
+    arena8 = FlatArena([enc8, dec8])
+    w16, b32, gw, gb, _ = arena8.linear_views([enc8.mean_fc.weight, enc8.log_var_fc.weight], [enc8.mean_fc.bias, enc8.log_var_fc.bias])
+    assert w16.shape == (16, 8) and torch.equal(w16[:8].float(), enc8.mean_fc.weight.detach().bfloat16().float())
+    assert torch.equal(w16[8:].float(), enc8.log_var_fc.weight.detach().bfloat16().float()) and torch.equal(b32[8:], enc8.log_var_fc.bias.detach())
+    gw.fill_(2.0)
+    assert float(enc8.log_var_fc.weight.grad.min()) == 2.0 and float(enc8.mean_fc.weight.grad.min()) == 2.0
     arena.flat.zero_()                               # parameters are views of the arena
     assert all(float(p.abs().sum()) == 0 for p in enc.parameters())
     assert all(p.grad.data_ptr() >= arena.grad.data_ptr() for p in dec.parameters())
