@@ -67,7 +67,9 @@ def main():
                      "frac_of_measured_peak": round(gbs / peak, 4)})
         print(f"{name:28s} {str(shape):22s} {dtype:5s} {ms_med:9.4f} ms  {gbs:8.1f} GB/s  {gbs / peak:6.1%}", flush=True)
 
-    lat = [(32, 1 << 20), (64, 1 << 20), (64, 4 << 20), (64, 16 << 20), (256, 1 << 20), (256, 4 << 20), (1024, 1 << 20)]
+    # BASELINE configs[4]: latent dim 32-1024 x 1M-64M frames, capped at 2^31 elements per tensor (five live tensors)
+    lat = [(32, 1 << 20), (32, 16 << 20), (32, 64 << 20), (64, 1 << 20), (64, 4 << 20), (64, 16 << 20), (128, 1 << 20), (128, 4 << 20),
+           (128, 16 << 20), (256, 1 << 20), (256, 4 << 20), (512, 1 << 20), (512, 4 << 20), (1024, 1 << 20)]
     if args.quick:
         lat = [(64, 1 << 20), (64, 4 << 20), (256, 1 << 20)]
     if not args.only or "latent" in args.only:

@@ -73,6 +73,12 @@ size_t mlvae_reduce_scratch_bytes(void);
  * ------------------------------------------------------------------------- */
 int mlvae_philox_u32(uint64_t seed, uint64_t offset, int64_t n, uint32_t *d_out, void *stream);
 int mlvae_philox_normal(uint64_t seed, uint64_t offset, int64_t n, void *d_out, int dtype, void *stream);
+/* The float32 kernels draw 4 normals per Philox call from 32-bit uniforms; the bf16 kernels draw EIGHT per call from 16-bit
+ * uniforms (block i/8, word j -> pair (2j, 2j+1): u1 = (lo16+1) 2^-16, theta = (hi16-32768) pi/32768; oracle/philox_ref.py
+ * philox_normal_v2), which takes the bf16 reparameterisation kernel off the instruction-issue bound.  mlvae_philox_normal
+ * materialises the stream of the kernels of `dtype`; _ex separates the storage type from the kernel type whose stream is
+ * wanted (e.g. float32 values of the bf16 kernels' eps for a parity test). */
+int mlvae_philox_normal_ex(uint64_t seed, uint64_t offset, int64_t n, void *d_out, int out_dtype, int kernel_dtype, void *stream);
 
 /* ------------------------------------------------------------------------- *
  * Fused reparameterise + KL (+ length-masked mean).

@@ -37,6 +37,7 @@ SIGNATURES = {
     "mlvae_reduce_scratch_bytes": (_sz, []),
     "mlvae_philox_u32": (_i, [_u64, _u64, _i64, _vp, _vp]),
     "mlvae_philox_normal": (_i, [_u64, _u64, _i64, _vp, _i, _vp]),
+    "mlvae_philox_normal_ex": (_i, [_u64, _u64, _i64, _vp, _i, _i, _vp]),
     "mlvae_reparam_kl_fwd": (_i, [_vp, _vp, _vp, _u64, _u64, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "mlvae_reparam_kl_bwd": (_i, [_vp, _vp, _vp, _u64, _u64, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "mlvae_gmm_reparam_kl_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _u64, _u64, _vp, _i64, _i, _vp, _vp, _vp]),

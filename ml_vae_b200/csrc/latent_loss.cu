@@ -138,22 +138,35 @@ __global__ void __launch_bounds__(kThreads) philox_u32_kernel(uint64_t seed, uin
     }
 }
 
-template <typename T>
+// kV2: the eps stream of the bf16 kernels (8 normals per Philox call, philox.cuh) instead of the float32 kernels' stream
+template <typename T, bool kV2>
 __global__ void __launch_bounds__(kThreads) philox_normal_kernel(uint64_t seed, uint64_t offset, int64_t n, T *out) {
     const PhiloxKey key(seed);
-    const int64_t nblk = (n + 3) / 4;
+    constexpr int PB = kV2 ? 8 : 4;
+    const int64_t nblk = (n + PB - 1) / PB;
     for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nblk; q += (int64_t)gridDim.x * blockDim.x) {
-        float v[4];
-        philox_normal4((uint64_t)q, offset, key, v);
-        for (int k = 0; k < 4; ++k)
-            if (4 * q + k < n) out[4 * q + k] = from_f32<T>(v[k]);
+        float v[8];
+        if constexpr (kV2) philox_normal8((uint64_t)q, offset, key, v);
+        else philox_normal4((uint64_t)q, offset, key, v);
+        for (int k = 0; k < PB; ++k)
+            if (PB * q + k < n) out[PB * q + k] = from_f32<T>(v[k]);
     }
 }
 
-// eps for VEC (= 1, 4 or 8) consecutive stream elements starting at element e0.
-template <int VEC>
+// eps for VEC (= 1, 4 or 8) consecutive stream elements starting at element e0: the float32 kernels draw the v1 stream
+// (4 normals per Philox call), the bf16 kernels the v2 stream (8 per call).
+template <typename T, int VEC>
 __device__ __forceinline__ void stream_eps(int64_t e0, uint64_t offset, const PhiloxKey &key, float *eps) {
-    if constexpr (VEC == 1) {
+    if constexpr (sizeof(T) == 2) {
+        if constexpr (VEC == 8) {
+            philox_normal8((uint64_t)e0 >> 3, offset, key, eps);
+        } else {
+            static_assert(VEC == 1, "bf16 kernels are instantiated with VEC = 8 or 1");
+            float v[8];
+            philox_normal8((uint64_t)e0 >> 3, offset, key, v);
+            eps[0] = v[e0 & 7];
+        }
+    } else if constexpr (VEC == 1) {
         float v[4];
         philox_normal4((uint64_t)e0 >> 2, offset, key, v);
         eps[0] = v[e0 & 3];
@@ -199,7 +212,7 @@ reparam_kl_fwd_kernel(const T *__restrict__ mu, const T *__restrict__ logvar, co
         m.load(mu + e0);
         lv.load(logvar + e0);
         if (eps) ep.load(eps + e0);
-        else stream_eps<VEC>(e0, offset, key, ep.v);
+        else stream_eps<T, VEC>(e0, offset, key, ep.v);
         float maskf = 1.f;
         if (kl_out) maskf = ((float)w.t < mask_threshold(__ldg(lens + w.b), Tn)) ? 1.f : 0.f;
         float part = 0.f;
@@ -236,7 +249,7 @@ reparam_kl_bwd_kernel(const T *__restrict__ mu, const T *__restrict__ logvar, co
         if (grad_z) gz.load(grad_z + e0); else gz.zero();
         if (grad_kl_elem) ge.load(grad_kl_elem + e0); else ge.zero();
         if (eps) ep.load(eps + e0);
-        else stream_eps<VEC>(e0, offset, key, ep.v);
+        else stream_eps<T, VEC>(e0, offset, key, ep.v);
         float gm_row = 0.f;
         if (grad_kl_mean) gm_row = gscale * (((float)w.t < mask_threshold(__ldg(lens + w.b), Tn)) ? 1.f : 0.f);
 #pragma unroll
@@ -407,7 +420,7 @@ gmm_reparam_kl_fwd_kernel(const T *__restrict__ mu, const T *__restrict__ logvar
         Chunk<T, VEC> m, lv, pm, plv, ep, zz, kk;
         m.load(mu + e0); lv.load(logvar + e0); pm.load(pmu + e0); plv.load(plogvar + e0);
         if (eps) ep.load(eps + e0);
-        else stream_eps<VEC>(e0, offset, key, ep.v);
+        else stream_eps<T, VEC>(e0, offset, key, ep.v);
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
             const float sd = fast_exp<T>(0.5f * lv.v[i]);
@@ -436,7 +449,7 @@ gmm_reparam_kl_bwd_kernel(const T *__restrict__ mu, const T *__restrict__ logvar
         if (grad_z) gz.load(grad_z + e0); else gz.zero();
         if (grad_kl) gk.load(grad_kl + e0); else gk.zero();
         if (eps) ep.load(eps + e0);
-        else stream_eps<VEC>(e0, offset, key, ep.v);
+        else stream_eps<T, VEC>(e0, offset, key, ep.v);
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
             const float sd = fast_exp<T>(0.5f * lv.v[i]);
@@ -615,15 +628,27 @@ int mlvae_philox_u32(uint64_t seed, uint64_t offset, int64_t n, uint32_t *d_out,
     return MLVAE_OK;
 }
 
-int mlvae_philox_normal(uint64_t seed, uint64_t offset, int64_t n, void *d_out, int dtype, void *stream) {
+int mlvae_philox_normal_ex(uint64_t seed, uint64_t offset, int64_t n, void *d_out, int out_dtype, int kernel_dtype, void *stream) {
     MLVAE_REQUIRE(d_out && n >= 0, MLVAE_ERR_INVALID_ARG, "philox_normal: bad arguments");
+    MLVAE_REQUIRE((out_dtype == MLVAE_F32 || out_dtype == MLVAE_BF16) && (kernel_dtype == MLVAE_F32 || kernel_dtype == MLVAE_BF16), MLVAE_ERR_INVALID_ARG,
+                  "philox_normal: unknown dtype");
     if (n == 0) return MLVAE_OK;
     const int g = grid_for((n + 3) / 4);
-    if (dtype == MLVAE_F32) philox_normal_kernel<float><<<g, kThreads, 0, (cudaStream_t)stream>>>(seed, offset, n, (float *)d_out);
-    else if (dtype == MLVAE_BF16) philox_normal_kernel<__nv_bfloat16><<<g, kThreads, 0, (cudaStream_t)stream>>>(seed, offset, n, (__nv_bfloat16 *)d_out);
-    else return fail(MLVAE_ERR_INVALID_ARG, "unknown dtype %d", dtype);
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool v2 = kernel_dtype == MLVAE_BF16;
+    if (out_dtype == MLVAE_F32) {
+        if (v2) philox_normal_kernel<float, true><<<g, kThreads, 0, st>>>(seed, offset, n, (float *)d_out);
+        else philox_normal_kernel<float, false><<<g, kThreads, 0, st>>>(seed, offset, n, (float *)d_out);
+    } else {
+        if (v2) philox_normal_kernel<__nv_bfloat16, true><<<g, kThreads, 0, st>>>(seed, offset, n, (__nv_bfloat16 *)d_out);
+        else philox_normal_kernel<__nv_bfloat16, false><<<g, kThreads, 0, st>>>(seed, offset, n, (__nv_bfloat16 *)d_out);
+    }
     MLVAE_CHECK_CUDA(cudaGetLastError());
     return MLVAE_OK;
+}
+
+int mlvae_philox_normal(uint64_t seed, uint64_t offset, int64_t n, void *d_out, int dtype, void *stream) {
+    return mlvae_philox_normal_ex(seed, offset, n, d_out, dtype, dtype, stream);      // the stream the kernels of that dtype draw
 }
 
 int mlvae_reparam_kl_fwd(const void *d_mu, const void *d_logvar, const void *d_eps, uint64_t seed, uint64_t offset,

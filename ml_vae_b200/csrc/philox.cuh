@@ -51,4 +51,30 @@ __device__ __forceinline__ void philox_normal4(uint64_t q, uint64_t offset, cons
     box_muller(r.z, r.w, out[2], out[3]);
 }
 
+// ---- eps stream of the bf16 kernels ("v2"): EIGHT normals per Philox call ------------------------------------------------
+// The float32 stream above spends one Philox4x32-10 call (~60 integer instructions) per 4 normals, which makes the bf16
+// reparameterisation kernel instruction-issue bound at ~50 % of the HBM roofline (profiles/r01_reparam_ncu_raw.csv).  The bf16
+// kernels therefore draw 16-bit uniforms: block q = element / 8, word j of the block gives the pair (2j, 2j+1):
+//   u1 = (lo16 + 1) * 2^-16 in (0, 1],   theta = (hi16 - 32768) * (pi / 32768) in [-pi, pi)
+//   n_even = r cos(theta), n_odd = r sin(theta), r = sqrt(-2 ln u1)        (|n| <= 4.71; 2^32 distinct pairs)
+// Host restatement: oracle/philox_ref.py philox_normal_v2.
+__device__ __forceinline__ void box_muller16(uint32_t w, float &n0, float &n1) {
+    const float u1 = __uint2float_rn((w & 0xffffu) + 1u) * 1.52587890625e-05f;
+    const float th = __int2float_rn((int)(w >> 16) - 32768) * 9.587379924285257e-05f;
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-2.0f * __logf(u1)));
+    float s, c;
+    __sincosf(th, &s, &c);
+    n0 = r * c;
+    n1 = r * s;
+}
+// 8 consecutive normals of the v2 stream: elements [8q, 8q+8).
+__device__ __forceinline__ void philox_normal8(uint64_t q, uint64_t offset, const PhiloxKey &key, float out[8]) {
+    const uint4 r = philox4x32_10(make_uint4((uint32_t)q, (uint32_t)(q >> 32), (uint32_t)offset, (uint32_t)(offset >> 32)), key);
+    box_muller16(r.x, out[0], out[1]);
+    box_muller16(r.y, out[2], out[3]);
+    box_muller16(r.z, out[4], out[5]);
+    box_muller16(r.w, out[6], out[7]);
+}
+
 }  // namespace mlvae

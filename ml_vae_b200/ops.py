@@ -32,11 +32,14 @@ def _lens(lens: torch.Tensor, like: torch.Tensor) -> torch.Tensor:
     return lens.to(device=like.device, dtype=torch.float32).contiguous()
 
 
-def philox_normal(shape, seed: int, offset: int = 0, dtype=torch.float32, device="cuda") -> torch.Tensor:
-    """Materialise the eps stream the fused kernel would draw for (seed, offset)."""
+def philox_normal(shape, seed: int, offset: int = 0, dtype=torch.float32, device="cuda", kernel_dtype=None) -> torch.Tensor:
+    """Materialise the eps stream the fused kernels draw for (seed, offset).  The float32 and the bf16 kernels draw different
+    streams (4 vs 8 normals per Philox call, csrc/philox.cuh): ``kernel_dtype`` (default: ``dtype``) says whose; e.g.
+    ``philox_normal(shape, s, o, kernel_dtype=torch.bfloat16)`` = float32 values of what the bf16 kernels used."""
     out = torch.empty(shape, dtype=dtype, device=device)
     L.require_cuda(out)
-    L.check(L.lib().mlvae_philox_normal(seed, offset, out.numel(), L.ptr(out), L.dtype_code(out), L.stream_ptr()),
+    kd = L.dtype_code(out) if kernel_dtype is None else (L.BF16 if kernel_dtype == torch.bfloat16 else L.F32)
+    L.check(L.lib().mlvae_philox_normal_ex(seed, offset, out.numel(), L.ptr(out), L.dtype_code(out), kd, L.stream_ptr()),
             "mlvae_philox_normal")
     return out
 

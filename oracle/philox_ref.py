@@ -77,6 +77,30 @@ def philox_normal(seed: int, offset: int, n: int, dtype=np.float32) -> np.ndarra
     return out.reshape(-1)[:n].astype(dtype)
 
 
+def philox_normal_v2(seed: int, offset: int, n: int, dtype=np.float32) -> np.ndarray:
+    """eps stream of the bf16 kernels (csrc/philox.cuh "v2"): EIGHT normals per Philox block from 16-bit uniforms.
+    Element i: block q = i // 8 (counter (q, offset), key seed), word j = (i % 8) // 2 of the block gives the pair (2j, 2j+1):
+      u1 = (lo16 + 1) * 2^-16 in (0, 1];  theta = (hi16 - 32768) * fl32(pi / 32768);  r = sqrt(-2 ln u1)
+      n_even = r cos(theta), n_odd = r sin(theta)
+    evaluated in float64 from the same float32 u1 / theta as the kernel (which uses the GPU's fast approximations)."""
+    nblk = (n + 7) // 8
+    q = np.arange(nblk, dtype=np.uint64)
+    ctr = np.stack([q & MASK, q >> np.uint64(32),
+                    np.full(nblk, offset & 0xFFFFFFFF, np.uint64),
+                    np.full(nblk, (offset >> 32) & 0xFFFFFFFF, np.uint64)], -1).astype(np.uint32)
+    key = np.empty((nblk, 2), np.uint32)
+    key[:, 0] = seed & 0xFFFFFFFF
+    key[:, 1] = (seed >> 32) & 0xFFFFFFFF
+    w = philox4x32_10(ctr, key)                                   # (nblk, 4)
+    lo = (w & np.uint32(0xFFFF)).astype(np.float32)
+    hi = (w >> np.uint32(16)).astype(np.int64)
+    u1 = ((lo + np.float32(1.0)) * np.float32(2.0 ** -16)).astype(np.float64)
+    theta = ((hi - 32768).astype(np.float32) * np.float32(np.pi / 32768.0)).astype(np.float64)
+    rad = np.sqrt(-2.0 * np.log(u1))
+    out = np.stack([rad * np.cos(theta), rad * np.sin(theta)], -1)   # (nblk, 4, 2)
+    return out.reshape(-1)[:n].astype(dtype)
+
+
 def dropout_keep_mask(seed: int, offset: int, n: int, p: float) -> np.ndarray:
     """Keep mask (bool, n) of the inter-layer LSTM dropout (decoder.py:14-15, dropout=rnn_dropout) as the CUDA kernel
     csrc/dropout.cu draws it: element i uses the 16-bit lane i % 8 (word (i % 8) // 2, low half first) of the Philox

@@ -95,10 +95,23 @@ def test_philox_stream_bit_exact_and_reproducible(cuda):
     # different offset -> different eps
     z3, _, _ = ops.reparam_kl(mu, lv, lens=lens, eps=None, seed=99, offset=4)
     assert not torch.equal(z, z3)
-    # bf16 path draws the same stream (rounded)
-    zb, _, _ = ops.reparam_kl(mu.detach().bfloat16(), lv.detach().bfloat16(), lens=lens, seed=99, offset=3)
-    zr = vae_ref.reparameterize(mu.detach().bfloat16().double(), lv.detach().bfloat16().double(), eps.double())
+    # the bf16 kernels draw their own stream (8 normals per Philox call from 16-bit uniforms, csrc/philox.cuh v2): device
+    # materialisation == host restatement, and the fused bf16 kernel uses exactly that stream (forward and backward)
+    for seed, offset, n in [(123456, 0, 4099), (2 ** 40 + 17, 2 ** 33 + 5, 1000), (0, 0, 7)]:
+        e2 = ops.philox_normal((n,), seed, offset, kernel_dtype=torch.bfloat16).cpu().numpy()
+        assert np.abs(e2 - philox_ref.philox_normal_v2(seed, offset, n)).max() < 5e-6
+    eps2 = ops.philox_normal((B, T, L), 99, 3, kernel_dtype=torch.bfloat16)                 # float32 values of the bf16 stream
+    assert not torch.equal(eps2, eps)
+    mub, lvb = mu.detach().bfloat16().requires_grad_(True), lv.detach().bfloat16().requires_grad_(True)
+    zb, _, klb = ops.reparam_kl(mub, lvb, lens=lens, seed=99, offset=3)
+    zr = vae_ref.reparameterize(mub.detach().double(), lvb.detach().double(), eps2.double())
     assert_close(zb.float(), zr, BF16_RTOL, "bf16 philox z")
+    gb = torch.autograd.grad(zb.float().sum() + klb, [mub, lvb])
+    mur, lvr = mub.detach().double().cpu().requires_grad_(True), lvb.detach().double().cpu().requires_grad_(True)
+    tot = vae_ref.reparameterize(mur, lvr, eps2.double().cpu()).sum() + vae_ref.masked_reduce(vae_ref.kld_elementwise(mur, lvr), lens.double().cpu())
+    gr = torch.autograd.grad(tot, [mur, lvr])
+    assert_close(gb[0].float(), gr[0], BF16_RTOL, "bf16 philox grad_mu")
+    assert_close(gb[1].float(), gr[1], BF16_RTOL, "bf16 philox grad_logvar")          # 0.5 exp(0.5 lv) eps: carries the stream
 
 
 @pytest.mark.parametrize("B,T,D", [(3, 21, 120), (4, 30, 80), (2, 9, 7), (8, 300, 240), (1, 1, 1)])

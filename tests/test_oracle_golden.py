@@ -121,6 +121,15 @@ def test_philox_known_answers():
         assert [int(v) for v in got] == want
 
 
+def test_philox_normal_v2_moments():
+    """The bf16 kernels' stream (16-bit uniforms, 8 normals per Philox block): standard normal to 4 moments, |n| <= 4.71."""
+    e = philox_ref.philox_normal_v2(123456, 0, 1 << 18).astype(np.float64)
+    assert abs(e.mean()) < 6e-3 and abs(e.std() - 1) < 6e-3
+    assert abs((e ** 3).mean()) < 3e-2 and abs((e ** 4).mean() - 3) < 6e-2
+    assert np.abs(e).max() <= np.sqrt(-2 * np.log(2.0 ** -16)) + 1e-6
+    assert not np.array_equal(e[:16], philox_ref.philox_normal(123456, 0, 16))
+
+
 def test_philox_normal_moments():
     e = philox_ref.philox_normal(123456, 0, 1 << 18).astype(np.float64)
     assert abs(e.mean()) < 0.01 and abs(e.std() - 1) < 0.01

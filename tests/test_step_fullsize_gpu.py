@@ -100,7 +100,7 @@ def _run(cuda, B, seconds, latent, p_drop, seed=1234):
     assert f_ref.shape[1] == T
     rel_ref = frames.float() / T
     x = vae_ref.GlobalNormRef()(f_ref, rel_ref)
-    eps = ops.philox_normal((B, T, latent), seed, 0).cpu()
+    eps = ops.philox_normal((B, T, latent), seed, 0, kernel_dtype=torch.bfloat16).cpu()     # float32 values of the bf16 kernels' stream
     masks = None
     if p_drop > 0:
         keep = philox_ref.dropout_keep_mask(dec.dropout_seed, 0, B * T * 2 * H, p_drop).reshape(B, T, 2 * H)
