@@ -296,6 +296,47 @@ size_t mlvae_gemm_workspace_bytes(int nprob, int M, int N, int split_k);
 int mlvae_gemm_bf16(const mlvae_gemm_args *args, void *stream);
 
 /* ------------------------------------------------------------------------- *
+ * Fused two-layer Linear / LeakyReLU(0.01) chain (csrc/mlp_chain.cu): modules/fc_block.py:4-21 as used by the encoder trunk
+ * (modules/vanilla_vae.py:13-24, D -> 64 -> 64, both layers activated) and by the tails of the decoder heads
+ * (modules/decoder.py:16-17,24-25, 64 -> 64 -> D, last layer bare; both heads = nprob 2 in one launch).
+ *   forward   y_a = LeakyReLU(x W_a^T + b_a)  (saved for the backward pass if y_a != NULL),  y_b = act_b(y_a W_b^T + b_b)
+ *   backward  g_b = g_out * act_b'(y_b);  dW_b += g_b^T y_a;  db_b += colsum g_b;  g_a = (g_b W_b) * LeakyReLU'(y_a);
+ *             dW_a += g_a^T x;  db_a += colsum g_a;  dx = g_a W_a  (dx may be NULL)
+ * A 128-row tile of the batch goes through both layers on chip (TMA -> tcgen05 -> TMEM -> shared-memory operand tile ->
+ * tcgen05); the weight / bias gradients accumulate in tensor memory over the tiles of a CTA and are reduced in CTA order.
+ * bf16 activations and weights (row-major W (N, K) as nn.Linear stores them, contiguous), float32 biases and gradients.
+ * Widths: multiples of 16, K_A, N_A <= 112, N_B <= 128.  Every matrix 16-byte aligned with its leading dimension % 8 == 0.
+ * ------------------------------------------------------------------------- */
+typedef struct mlvae_chain_fwd_args {
+    int nprob;              /* 1 or 2 independent chains of the same shape */
+    const void *x[2];       /* (M, K_A) bf16, row stride ld_x */
+    const void *w_a[2];     /* (N_A, K_A) bf16 */
+    const void *w_b[2];     /* (N_B, N_A) bf16 */
+    const float *bias_a[2], *bias_b[2];
+    void *y_a[2];           /* (M, N_A) bf16, row stride ld_ya; NULL: not stored */
+    void *y_b[2];           /* (M, N_B) bf16, row stride ld_yb */
+    int M, K_A, N_A, N_B, act_b;
+    int64_t ld_x, ld_ya, ld_yb;
+} mlvae_chain_fwd_args;
+int mlvae_mlp_chain_fwd(const mlvae_chain_fwd_args *args, void *stream);
+
+typedef struct mlvae_chain_bwd_args {
+    int nprob;
+    const void *g_out[2];   /* (M, N_B) bf16 gradient of the chain output, row stride ld_g */
+    const void *y_b[2];     /* (M, N_B) chain output, row stride ld_yb; only read when act_b */
+    const void *y_a[2];     /* (M, N_A) hidden activation saved by the forward pass, row stride ld_ya */
+    const void *x[2];       /* (M, K_A) chain input, row stride ld_x */
+    const void *w_a[2], *w_b[2];
+    float *dw_a[2], *db_a[2], *dw_b[2], *db_b[2];   /* float32, ACCUMULATED into */
+    void *dx[2];            /* (M, K_A) bf16, row stride ld_dx, or NULL */
+    int M, K_A, N_A, N_B, act_b;
+    int64_t ld_g, ld_yb, ld_ya, ld_x, ld_dx;
+    void *ws;               /* mlvae_mlp_chain_bwd_workspace_bytes(nprob, K_A, N_A) bytes */
+} mlvae_chain_bwd_args;
+size_t mlvae_mlp_chain_bwd_workspace_bytes(int nprob, int K_A, int N_A);
+int mlvae_mlp_chain_bwd(const mlvae_chain_bwd_args *args, void *stream);
+
+/* ------------------------------------------------------------------------- *
  * Inter-layer dropout of the stacked LSTM (modules/decoder.py:14-15: nn.LSTM(..., dropout=rnn_dropout),
  * models/test_vanilla_vae/model.yaml dec_rnn_dropout: 0.15), with a reproducible counter-based mask instead
  * of torch's stateful generator.  y = keep ? x / (1 - p) : 0; element i keeps iff the 16-bit lane i % 8

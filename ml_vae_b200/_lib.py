@@ -29,6 +29,21 @@ class GemmArgs(C.Structure):
                 ("drop_p", C.c_float), ("drop_seed", _u64), ("drop_offset", _u64), ("drop_offset_add", _vp), ("bn", _i)]
 
 
+class ChainFwdArgs(C.Structure):
+    """mlvae_chain_fwd_args (include/mlvae_b200.h)."""
+    _fields_ = [("nprob", _i), ("x", _vp * 2), ("w_a", _vp * 2), ("w_b", _vp * 2), ("bias_a", _vp * 2), ("bias_b", _vp * 2),
+                ("y_a", _vp * 2), ("y_b", _vp * 2), ("M", _i), ("K_A", _i), ("N_A", _i), ("N_B", _i), ("act_b", _i),
+                ("ld_x", _i64), ("ld_ya", _i64), ("ld_yb", _i64)]
+
+
+class ChainBwdArgs(C.Structure):
+    """mlvae_chain_bwd_args (include/mlvae_b200.h)."""
+    _fields_ = [("nprob", _i), ("g_out", _vp * 2), ("y_b", _vp * 2), ("y_a", _vp * 2), ("x", _vp * 2), ("w_a", _vp * 2), ("w_b", _vp * 2),
+                ("dw_a", _vp * 2), ("db_a", _vp * 2), ("dw_b", _vp * 2), ("db_b", _vp * 2), ("dx", _vp * 2),
+                ("M", _i), ("K_A", _i), ("N_A", _i), ("N_B", _i), ("act_b", _i),
+                ("ld_g", _i64), ("ld_yb", _i64), ("ld_ya", _i64), ("ld_x", _i64), ("ld_dx", _i64), ("ws", _vp)]
+
+
 # name -> (restype, argtypes); mirrors include/mlvae_b200.h one to one
 SIGNATURES = {
     "mlvae_abi_version": (_i, []),
@@ -73,6 +88,9 @@ SIGNATURES = {
     "mlvae_tc05_selftest": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "mlvae_gemm_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "mlvae_gemm_bf16": (_i, [C.POINTER(GemmArgs), _vp]),
+    "mlvae_mlp_chain_fwd": (_i, [C.POINTER(ChainFwdArgs), _vp]),
+    "mlvae_mlp_chain_bwd_workspace_bytes": (_sz, [_i, _i, _i]),
+    "mlvae_mlp_chain_bwd": (_i, [C.POINTER(ChainBwdArgs), _vp]),
     "mlvae_dropout": (_i, [_vp, _vp, _i64, C.c_float, _u64, _u64, _vp, _i, _vp]),
     "mlvae_fbank_fwd": (_i, [_vp, _vp, _vp, _i, _i64, _i64, _i, _vp, _i, _i, _vp, _vp, _vp]),
 }

@@ -15,7 +15,7 @@ from __future__ import annotations
 import torch
 from torch import nn
 
-from .. import lstm, ops
+from .. import lstm, mlp_chain, ops
 from ..dense import direct_chain, linear, linear_chain, linear_direct
 from ._params import attach, torch_default_linear, torch_default_lstm
 
@@ -127,8 +127,13 @@ class Decoder(nn.Module):
             head0, mviews, vviews = direct
             n0 = wm[0].shape[0]
             h0 = linear_direct(rnn_out, head0, leaky=True)
-            mean = direct_chain(h0[..., :n0], mviews)
-            log_var = direct_chain(h0[..., n0:], vviews)
+            if (len(mviews) == 2 and len(vviews) == 2 and mviews[0][0].shape == vviews[0][0].shape and mviews[1][0].shape == vviews[1][0].shape
+                    and mlp_chain.supported(n0, mviews[0][0].shape[0], mviews[1][0].shape[0])):
+                # the tails of BOTH heads (64 -> 64 -> D each) in one fused launch per pass (csrc/mlp_chain.cu)
+                mean, log_var = mlp_chain.chain2(h0, [mviews[0], vviews[0]], [mviews[1], vviews[1]], act_b=False)
+            else:
+                mean = direct_chain(h0[..., :n0], mviews)
+                log_var = direct_chain(h0[..., n0:], vviews)
         elif len(wm) > 1 and wm[0].shape == wv[0].shape:
             # both heads read the (B, T, 2H) LSTM output: their first layers run as ONE GEMM against the stacked
             # weight, so the widest activation of the model is read once (decoder.py:24-25 reads it twice)

@@ -18,7 +18,7 @@ from __future__ import annotations
 import torch
 from torch import nn
 
-from .. import ops
+from .. import mlp_chain, ops
 from ..dense import LEAKY_SLOPE, direct_chain, linear_chain, linear_direct
 from ._params import attach, torch_default_linear
 
@@ -76,7 +76,10 @@ class VanillaVAE(nn.Module):
         direct = getattr(self, "_direct", None)
         if direct is not None and feats.dtype == torch.bfloat16:
             trunk, heads = direct
-            h = direct_chain(feats, trunk, end_activation=True)
+            if len(trunk) == 2 and mlp_chain.supported(trunk[0][0].shape[1], trunk[0][0].shape[0], trunk[1][0].shape[0]):
+                h, = mlp_chain.chain2(feats, [trunk[0]], [trunk[1]], act_b=True)      # fused trunk (csrc/mlp_chain.cu)
+            else:
+                h = direct_chain(feats, trunk, end_activation=True)
             ml = linear_direct(h, heads)
             mean, log_var = ml[..., : self.latent_size], ml[..., self.latent_size:]
             return mean.contiguous(), log_var.contiguous()
