@@ -25,7 +25,8 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-LIBRARY_CALLS = "time-parallel GEMMs (LSTM input projection / dX / dW, dense dW) are cuBLAS through torch"
+LIBRARY_CALLS = ("none in the bf16 step: every contraction runs on kernels of libmlvae_b200.so (lstm_fwd/bwd_kernel, gemm_bf16_kernel, "
+                 "chain2_fwd/bwd_kernel, linear_fwd_kernel); tests/test_kernel_provenance_gpu.py asserts it from the profiler's kernel names")
 METRIC = "train_utterances_per_sec_fwd_bwd"
 UNIT = "utt/s"
 WORKLOADS = {
@@ -198,6 +199,29 @@ def traffic_source(config):
     return None if r is None else r["source"]
 
 
+def embedded_runs():
+    """The other BASELINE configs, run by the driver's plain `python bench.py` too (N = 1 only, a few seconds each, own
+    processes so that nothing of the headline measurement is shared): configs[3] through the same step, and the corners of the
+    configs[4] kernel sweep."""
+    out = {}
+    py = sys.executable
+    try:
+        r = subprocess.run([py, os.path.join(ROOT, "bench.py"), "--config", "c4", "--steps", "10", "--warmup", "3", "--no-cpu-baseline", "--no-extra"],
+                           capture_output=True, text=True, timeout=240)
+        d = json.loads(r.stdout.strip().splitlines()[-1])
+        out["configs3_long_utterances"] = {k: d[k] for k in ("metric", "value", "unit", "ms_per_step", "steps", "warmup", "config", "e2e", "clocks", "cuda_graph")}
+        out["configs3_long_utterances"]["kernels"] = {k: v for k, v in d["kernels"].items() if "lstm" in k}
+    except Exception as exc:                                   # the headline line must not depend on the extras
+        out["configs3_long_utterances"] = {"error": repr(exc)[:200]}
+    try:
+        r = subprocess.run([py, os.path.join(ROOT, "bench_kernels.py"), "--embedded"], capture_output=True, text=True, timeout=240)
+        row = [l for l in r.stdout.splitlines() if l.startswith("EMBEDDED_JSON ")][-1]
+        out["configs4_kernel_sweep"] = json.loads(row[len("EMBEDDED_JSON "):])
+    except Exception as exc:
+        out["configs4_kernel_sweep"] = {"error": repr(exc)[:200]}
+    return out
+
+
 def workload_config(n_gpus, batch_per_gpu):
     W = WORKLOAD
     T = frames_per_utt(W)
@@ -319,6 +343,7 @@ def run_ours(args):
         return ts.normalizer(feats, rel, epoch=ts.epoch).to(ts.dtype), rel
 
     ts.features = probed_features
+    from ml_vae_b200 import gemm as gemm_mod
     from ml_vae_b200 import lstm as lstm_mod
     lstm_mod.PROBE = []
     L.LAUNCHES = 0
@@ -335,6 +360,7 @@ def run_ours(args):
         L.LAUNCHES = 0
         fb_evs.clear()
         lstm_mod.PROBE = []
+        gemm_mod.PROBE = []
         probe_steps = 4
         for i in range(probe_steps):
             ts._step_eager(resident[i % R], lens_abs)
@@ -347,6 +373,8 @@ def run_ours(args):
     for tag, a, b in lstm_mod.PROBE:
         lstm_ms.setdefault(tag, []).append(a.elapsed_time(b))
     lstm_mod.PROBE = None
+    gemm_evs = [(f, a.elapsed_time(b)) for f, a, b in (gemm_mod.PROBE or [])]
+    gemm_mod.PROBE = None
 
     e2e_steps = [max(1, args.warmup // 2)]
     for i in range(e2e_steps[0]):
@@ -367,6 +395,14 @@ def run_ours(args):
                                                 "achieved_gbs": round(fb_bytes / (fb_ms * 1e-3) / 1e9, 1),
                                                 "frac_of_hbm_peak": round(fb_bytes / (fb_ms * 1e-3) / 1e9 / peak, 4),
                                                 "share_of_step": round(fb_ms / step_ms, 4)}}
+    if gemm_evs:
+        g_ms = sum(ms for _, ms in gemm_evs) / probe_steps
+        g_fl = sum(f for f, _ in gemm_evs) / probe_steps
+        kernels["gemm_bf16_kernel(all TMA/tcgen05 GEMMs of the step)"] = {
+            "ms_per_step": round(g_ms, 4), "launches_per_step": len(gemm_evs) // probe_steps, "bound": "tensor", "algorithmic_flops_per_step": g_fl,
+            "achieved_tflops": round(g_fl / (g_ms * 1e-3) / 1e12, 1), "frac_of_bf16_sustained_peak": round(g_fl / (g_ms * 1e-3) / 1e12 / tflops_peak, 4),
+            "share_of_step": round(g_ms / step_ms, 4),
+            "note": "event pairs around each launch incl. the split-K second pass; the skinny dense-gradient GEMMs are HBM / latency bound"}
     if lstm_ms:
         # dominant hand-written kernels: the persistent LSTM recurrences (one launch per layer and pass, both directions)
         flops = 2.0 * B * T_frames * (4 * H) * H * 2                     # h W_hh^T (fwd) or dA W_hh (bwd), two directions
@@ -412,6 +448,8 @@ def run_ours(args):
                                     "sample": f"full {B} x {W['seconds']:g} s batch per step, 1 warm-up + 3 timed fwd+bwd+clip+Adam steps "
                                               "of the oracle port (restated SpeechBrain Fbank + reference VAE modules, LSTM dropout "
                                               "0.15), fp32, all host cores"}
+        if world == 1 and not args.no_extra and args.config == "c2":
+            line["extra"] = embedded_runs()
         emit(line)
     if world > 1:
         # release the captured graph (it references the communicator) before tearing the process group down, and do
@@ -454,6 +492,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--config", default="c2", choices=sorted(WORKLOADS), help="c2 = BASELINE configs[1] (default), c4 = configs[3]")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the embedded configs[3] run and configs[4] kernel sweep (N = 1 default run only)")
     ap.add_argument("--profile", default="", help="write a torch.profiler kernel table of 3 steps to this path")
     ap.add_argument("--no-graph", action="store_true", help="do not capture the step in a CUDA graph")
     ap.add_argument("--overlap", action="store_true", help="all-reduce the tail of the gradient bucket under the first LSTM layer's backward (measured slower at N=2)")

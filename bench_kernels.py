@@ -47,6 +47,7 @@ def time_ms(fn, flush, iters=10, warm=3):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--embedded", action="store_true", help="the subset bench.py embeds in its JSON line (configs[4] corners, a few seconds)")
     ap.add_argument("--out", default="")
     ap.add_argument("--only", default="")
     args = ap.parse_args()
@@ -72,6 +73,8 @@ def main():
            (128, 16 << 20), (256, 1 << 20), (256, 4 << 20), (512, 1 << 20), (512, 4 << 20), (1024, 1 << 20)]
     if args.quick:
         lat = [(64, 1 << 20), (64, 4 << 20), (256, 1 << 20)]
+    if args.embedded:
+        lat = [(32, 64 << 20), (64, 1 << 20), (64, 16 << 20), (128, 4 << 20), (512, 4 << 20), (1024, 1 << 20)]
     if not args.only or "latent" in args.only:
         for dt, s, name in ((torch.bfloat16, 2, "bf16"), (torch.float32, 4, "f32")):
             for Ld, M in lat:
@@ -118,6 +121,12 @@ def main():
                 del mu, lv, gz, z, gmu, glv
                 torch.cuda.empty_cache()
 
+    if args.embedded:
+        if args.out:
+            os.makedirs(os.path.dirname(os.path.join(ROOT, args.out)) or ".", exist_ok=True)
+            json.dump({"peak_gbs": peak, "rows": rows}, open(os.path.join(ROOT, args.out), "w"), indent=1)
+        print("EMBEDDED_JSON " + json.dumps({"peak_gbs": peak, "cap": "shapes with more than 2^31 elements per tensor are skipped", "rows": rows}), flush=True)
+        return
     if not args.only or "fbank" in args.only:
         for (B, secs, hop_ms, mels, dl, od) in [(64, 5, 10, 80, False, torch.float32), (64, 5, 10, 80, True, torch.bfloat16),
                                                 (16, 20, 10, 80, False, torch.float32), (512, 5, 10, 80, False, torch.float32),

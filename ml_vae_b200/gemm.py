@@ -14,6 +14,7 @@ import torch
 from . import _lib as L
 
 _ws = {}
+PROBE = None      # bench.py sets this to a list; every GEMM launch then appends (flops, start_event, end_event)
 
 
 def _workspace(nbytes: int, device):
@@ -52,5 +53,13 @@ def gemm(A, B, D, M: int, N: int, K: int, *, lda: int, ldb: int, ldd: int, a_mn:
     a.drop_p, a.drop_seed, a.drop_offset = float(drop_p), drop_seed, drop_offset
     a.drop_offset_add = None if drop_offset_dev is None else drop_offset_dev.data_ptr()
     a.bn = bn
+    ev0 = None
+    if PROBE is not None:
+        ev0 = torch.cuda.Event(enable_timing=True)
+        ev0.record()
     L.check(L.lib().mlvae_gemm_bf16(C.byref(a), L.stream_ptr()), "mlvae_gemm_bf16", kernels=2 if split_k > 1 else 1)
+    if ev0 is not None:
+        ev1 = torch.cuda.Event(enable_timing=True)
+        ev1.record()
+        PROBE.append((2.0 * len(As) * M * N * K * kbatches, ev0, ev1))
     return D
