@@ -268,7 +268,7 @@ def run_ours(args):
     dec = Decoder(W["latent"], W["rnn_hidden"], W["rnn_layers"], W["rnn_dropout"],
                   [2 * W["rnn_hidden"], W["dec_fc"], W["dec_fc"], D]).to(dev)
     ts = TrainStep(fb, InputNormalization().to(dev), enc, dec, {"kld_weight": 0.001, "batch_size": B}, lr=1e-3,
-                   compute_dtype=dtype, world_size=world, overlap_all_reduce=args.overlap)
+                   compute_dtype=dtype, world_size=world, overlap_all_reduce=args.overlap, dp_mode=args.dp_mode)
 
     g = torch.Generator().manual_seed(123456 + rank)
     R = 4                                                       # distinct resident batches, rotated
@@ -441,6 +441,15 @@ def run_ours(args):
             "gpu_launches": int(round(launches)), "roofline": roof, "kernels": kernels,
             "library_calls": LIBRARY_CALLS,
             "clocks": clocks, "wall_s": round(wall, 3), "cuda_graph": graphed}
+    if world > 1:
+        if ts.dp_peer:
+            st = ts.arena.peer.read_state()
+            line["data_parallel"] = {"mode": "peer", "kernels": "dp_reduce_kernel + dp_adam_kernel (csrc/dp_optim.cu): gradient reduce-scatter, "
+                                     "sharded clip + Adam, parameter all-gather over NVLink peer memory; no NCCL call in the step",
+                                     "multicast": bool(ts.arena.peer.multicast_base), "optimizer_steps": st["step"], "sync_error": st["error"]}
+            line["config"]["parallelism"] += " (peer-memory reduce-scatter / sharded Adam / all-gather)"
+        else:
+            line["data_parallel"] = {"mode": "nccl", "kernels": "ncclAllReduce of the flat gradient bucket + adam_step_kernel on every rank"}
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             v, dt, cores = time_cpu_reference(B, 3, 1)
@@ -495,6 +504,9 @@ def main():
     ap.add_argument("--no-extra", action="store_true", help="skip the embedded configs[3] run and configs[4] kernel sweep (N = 1 default run only)")
     ap.add_argument("--profile", default="", help="write a torch.profiler kernel table of 3 steps to this path")
     ap.add_argument("--no-graph", action="store_true", help="do not capture the step in a CUDA graph")
+    ap.add_argument("--dp-mode", default="auto", choices=["auto", "peer", "nccl"],
+                    help="N > 1: peer = reduce-scatter + sharded Adam + all-gather kernels over NVLink peer memory (csrc/dp_optim.cu), "
+                         "nccl = NCCL all-reduce + full Adam on every rank, auto = peer when the node's symmetric memory is available")
     ap.add_argument("--overlap", action="store_true", help="all-reduce the tail of the gradient bucket under the first LSTM layer's backward (measured slower at N=2)")
     args = ap.parse_args()
     global WORKLOAD

@@ -253,7 +253,45 @@ int mlvae_dense_bwd_prep(const void *d_dy, const void *d_y, void *d_g, float *d_
  * ------------------------------------------------------------------------- */
 size_t mlvae_adam_state_bytes(void);
 int mlvae_adam_clip_step(float *d_params, float *d_grads, float *d_exp_avg, float *d_exp_avg_sq, void *d_params_bf16, int64_t n, float grad_scale,
-                         float lr, float beta1, float beta2, float eps, float max_grad_norm, void *d_state, const float *d_loss, void *stream);
+                         double lr, double beta1, double beta2, double eps, float max_grad_norm, void *d_state, const float *d_loss, void *stream);
+
+/* ------------------------------------------------------------------------- *
+ * Data-parallel optimiser step over NVLink peer memory (csrc/dp_optim.cu): what DDP around the reference does after
+ * loss.backward() -- all-reduce of every gradient, then check_gradients + Adam + zero_grad on EVERY rank
+ * (models/md_model.py:77-87) -- as a gradient reduce-scatter, a sharded clip + Adam and a parameter all-gather in two
+ * launches that load the peers' gradient arenas and store into the peers' parameter arenas directly:
+ *   rank r owns elements [r * ceil(n/4/world) * 4, ...) of the flat arena;
+ *   g[shard] = sum_ranks grads_r[shard] (fixed rank order);  norm = sqrt(sum over ranks of their shard's sum of squares of g / world);
+ *   clip / Adam as mlvae_adam_clip_step with grad_scale = 1 / world on the shard;  updated float32 parameters and bf16 shadow
+ *   stored into every rank's arrays;  the whole local gradient arena zeroed.
+ * grads[r] / params[r] / params_bf16[r] / sync[r]: rank r's arrays as mapped into THIS process (CUDA IPC or VMM peer
+ * mappings; entry [rank] is the local array).  sync[r]: mlvae_dp_sync_bytes() bytes, zeroed once before the first step, holds
+ * the inter-rank epoch flags and the Adam step count.  mc_*: optional multicast (NVLS) mappings of the same arrays; when
+ * given, the reduction is one multimem.ld_reduce and the parameter stores are multimem.st (set both or neither).
+ * exp_avg / exp_avg_sq: local, only the shard is touched.  loss: local device float or NULL; a non-finite loss on any rank
+ * (or a non-finite reduced gradient) skips the update on every rank.  Every rank must make the same calls in the same
+ * order; the two launches are CUDA-graph capturable.  A peer that never arrives sets the error flag after 20 s instead of
+ * hanging (mlvae_dp_read_state -> {epoch, adam step, last norm, last clip coefficient, error}).
+ * ------------------------------------------------------------------------- */
+#define MLVAE_DP_MAX_WORLD 8
+typedef struct mlvae_dp_adam_args {
+    int world, rank;
+    float *grads[MLVAE_DP_MAX_WORLD];
+    float *params[MLVAE_DP_MAX_WORLD];
+    void *params_bf16[MLVAE_DP_MAX_WORLD];     /* all NULL: no bf16 shadow */
+    void *sync[MLVAE_DP_MAX_WORLD];
+    float *mc_grads, *mc_params;
+    void *mc_params_bf16;
+    float *exp_avg, *exp_avg_sq;
+    int64_t n;
+    double lr, beta1, beta2, eps;              /* doubles like torch.optim.Adam's: 1 - beta is rounded to float32 once */
+    float max_grad_norm;
+    const float *loss;
+} mlvae_dp_adam_args;
+size_t mlvae_dp_sync_bytes(void);
+int mlvae_dp_adam_step(const mlvae_dp_adam_args *args, void *stream);
+int mlvae_dp_read_state(const void *d_sync, float out[5], void *stream);
+int mlvae_dp_debug_max_ctas(int n);          /* tests: cap both grids so that several ranks simulated on ONE device stay co-resident */
 
 /* ------------------------------------------------------------------------- *
  * TMA-fed tcgen05 GEMM (csrc/gemm.cu) for the time-parallel matrix products of the step -- what torch dispatches

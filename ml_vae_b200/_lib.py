@@ -44,6 +44,13 @@ class ChainBwdArgs(C.Structure):
                 ("ld_g", _i64), ("ld_yb", _i64), ("ld_ya", _i64), ("ld_x", _i64), ("ld_dx", _i64), ("ws", _vp)]
 
 
+class DpAdamArgs(C.Structure):
+    """mlvae_dp_adam_args (include/mlvae_b200.h)."""
+    _fields_ = [("world", _i), ("rank", _i), ("grads", _vp * 8), ("params", _vp * 8), ("params_bf16", _vp * 8), ("sync", _vp * 8),
+                ("mc_grads", _vp), ("mc_params", _vp), ("mc_params_bf16", _vp), ("exp_avg", _vp), ("exp_avg_sq", _vp), ("n", _i64),
+                ("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double), ("max_grad_norm", C.c_float), ("loss", _vp)]
+
+
 # name -> (restype, argtypes); mirrors include/mlvae_b200.h one to one
 SIGNATURES = {
     "mlvae_abi_version": (_i, []),
@@ -80,7 +87,11 @@ SIGNATURES = {
     "mlvae_dense_bwd_scratch_bytes": (C.c_size_t, [_i]),
     "mlvae_dense_bwd_prep": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i64, C.c_float, _vp, _i, _vp]),
     "mlvae_adam_state_bytes": (_sz, []),
-    "mlvae_adam_clip_step": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _vp, _vp, _vp]),
+    "mlvae_dp_sync_bytes": (_sz, []),
+    "mlvae_dp_adam_step": (_i, [C.POINTER(DpAdamArgs), _vp]),
+    "mlvae_dp_read_state": (_i, [_vp, C.POINTER(C.c_float * 5), _vp]),
+    "mlvae_dp_debug_max_ctas": (_i, [_i]),
+    "mlvae_adam_clip_step": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, C.c_float, C.c_double, C.c_double, C.c_double, C.c_double, C.c_float, _vp, _vp, _vp]),
     "mlvae_lstm_pack_weights": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp]),
     "mlvae_lstm_bias_grads": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "mlvae_lstm_unpack_grads": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),

@@ -11,6 +11,8 @@
 // Arithmetic follows torch.optim.Adam (fused, capturable) exactly, in float32:
 //   step += 1;  m += (g - m) (1 - b1);  v = b2 v + (1 - b2) g g;
 //   p -= (lr / (1 - b1^step)) * m / (sqrt(v) / sqrt(1 - b2^step) + eps)
+// with the hyper-parameters taken as DOUBLES like torch's (1 - b2 is rounded to float32 once from the double difference:
+// 1.f - 0.999f would be off by 1.3e-5 relative)
 // and torch.nn.utils.clip_grad_norm_:  g *= min(1, max_norm / (||g||_2 + 1e-6)).
 // Deterministic: per-CTA partial sums of squares, added in index order by every CTA of the second kernel.
 #include "common.cuh"
@@ -49,8 +51,9 @@ __global__ void __launch_bounds__(kOptThreads) grad_sumsq_kernel(const float *__
 
 __global__ void __launch_bounds__(kOptThreads) adam_step_kernel(float *__restrict__ p, float *__restrict__ g, float *__restrict__ m,
                                                                float *__restrict__ v, __nv_bfloat16 *__restrict__ p16, int64_t n, int npart,
-                                                               float gscale, float lr, float b1, float b2, float eps, float max_norm,
+                                                               float gscale, double lr, double b1d, double b2d, float eps, float max_norm,
                                                                AdamState *st, const float *__restrict__ loss) {
+    const float b2 = (float)b2d, omb1 = (float)(1.0 - b1d), omb2 = (float)(1.0 - b2d);
     __shared__ float s_coef;
     {   // every CTA adds the partials in the same order
         float a = 0.f;
@@ -69,8 +72,8 @@ __global__ void __launch_bounds__(kOptThreads) adam_step_kernel(float *__restric
     const float coef = s_coef;
     const float step = st->step;
     // bias corrections in double like torch's python-side arithmetic (once per thread)
-    const double bc1 = 1.0 - pow((double)b1, (double)step), bc2 = 1.0 - pow((double)b2, (double)step);
-    const float step_size = (float)((double)lr / bc1), bc2_sqrt = (float)sqrt(bc2);
+    const double bc1 = 1.0 - pow(b1d, (double)step), bc2 = 1.0 - pow(b2d, (double)step);
+    const float step_size = (float)(lr / bc1), bc2_sqrt = (float)sqrt(bc2);
     const int64_t n4 = n >> 2;
     for (int64_t i = (int64_t)blockIdx.x * kOptThreads + threadIdx.x; i < n4; i += (int64_t)gridDim.x * kOptThreads) {
         float4 pw = reinterpret_cast<float4 *>(p)[i];
@@ -81,8 +84,8 @@ __global__ void __launch_bounds__(kOptThreads) adam_step_kernel(float *__restric
             float pp[4] = {pw.x, pw.y, pw.z, pw.w}, mm[4] = {mw.x, mw.y, mw.z, mw.w}, vv[4] = {vw.x, vw.y, vw.z, vw.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                mm[e] = mm[e] + (gg[e] - mm[e]) * (1.f - b1);
-                vv[e] = vv[e] * b2 + (1.f - b2) * gg[e] * gg[e];
+                mm[e] = mm[e] + (gg[e] - mm[e]) * omb1;
+                vv[e] = vv[e] * b2 + omb2 * gg[e] * gg[e];
                 const float denom = sqrtf(vv[e]) / bc2_sqrt + eps;
                 pp[e] = pp[e] - step_size * (mm[e] / denom);
             }
@@ -101,8 +104,8 @@ __global__ void __launch_bounds__(kOptThreads) adam_step_kernel(float *__restric
         for (int64_t i = n4 << 2; i < n; ++i) {
             if (!skip) {
                 const float ge = g[i] * coef;
-                m[i] = m[i] + (ge - m[i]) * (1.f - b1);
-                v[i] = v[i] * b2 + (1.f - b2) * ge * ge;
+                m[i] = m[i] + (ge - m[i]) * omb1;
+                v[i] = v[i] * b2 + omb2 * ge * ge;
                 p[i] = p[i] - step_size * (m[i] / (sqrtf(v[i]) / bc2_sqrt + eps));
             }
             g[i] = 0.f;
@@ -121,7 +124,7 @@ extern "C" {
 size_t mlvae_adam_state_bytes(void) { return sizeof(AdamState); }
 
 int mlvae_adam_clip_step(float *d_params, float *d_grads, float *d_exp_avg, float *d_exp_avg_sq, void *d_params_bf16, int64_t n, float grad_scale,
-                         float lr, float beta1, float beta2, float eps, float max_grad_norm, void *d_state, const float *d_loss, void *stream) {
+                         double lr, double beta1, double beta2, double eps, float max_grad_norm, void *d_state, const float *d_loss, void *stream) {
     MLVAE_REQUIRE(d_params && d_grads && d_exp_avg && d_exp_avg_sq && d_state && n > 0, MLVAE_ERR_INVALID_ARG, "adam_clip_step: missing buffers");
     MLVAE_REQUIRE(((uintptr_t)d_params & 15) == 0 && ((uintptr_t)d_grads & 15) == 0 && ((uintptr_t)d_exp_avg & 15) == 0 &&
                       ((uintptr_t)d_exp_avg_sq & 15) == 0 && ((uintptr_t)d_params_bf16 & 7) == 0,
@@ -133,7 +136,7 @@ int mlvae_adam_clip_step(float *d_params, float *d_grads, float *d_exp_avg, floa
     grad_sumsq_kernel<<<grid, kOptThreads, 0, st>>>(d_grads, n, grad_scale, (AdamState *)d_state, d_loss);
     MLVAE_CHECK_CUDA(cudaGetLastError());
     adam_step_kernel<<<grid, kOptThreads, 0, st>>>(d_params, d_grads, d_exp_avg, d_exp_avg_sq, (__nv_bfloat16 *)d_params_bf16, n, grid, grad_scale, lr, beta1,
-                                                  beta2, eps, max_grad_norm, (AdamState *)d_state, d_loss);
+                                                  beta2, (float)eps, max_grad_norm, (AdamState *)d_state, d_loss);
     MLVAE_CHECK_CUDA(cudaGetLastError());
     return MLVAE_OK;
 }

@@ -47,7 +47,9 @@ class FlatArena:
 
     ALIGN = 8
 
-    def __init__(self, modules):
+    def __init__(self, modules, peer_memory=None):
+        """``peer_memory``: callable n -> peer.PeerArenaMemory (or None): the gradient / parameter / bf16 arrays are then views of
+        a symmetric allocation the other ranks of the node have mapped (data-parallel optimiser step over NVLink peer memory)."""
         params, seen = [], set()
         for m in modules:
             for p in m.parameters():
@@ -79,11 +81,15 @@ class FlatArena:
             off += p.numel()
         n = -(-off // self.ALIGN) * self.ALIGN
         dev = ordered[0].device
-        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
-        self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.peer = peer_memory(n, dev) if peer_memory is not None else None
+        if self.peer is not None:
+            self.flat, self.grad, self.flat_bf16 = self.peer.flat, self.peer.grad, self.peer.flat_bf16
+        else:
+            self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+            self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
+            self.flat_bf16 = torch.zeros(n, dtype=torch.bfloat16, device=dev)
         self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
-        self.flat_bf16 = torch.zeros(n, dtype=torch.bfloat16, device=dev)
         with torch.no_grad():
             for p in ordered:
                 o, k = self.offsets[id(p)], p.numel()
@@ -144,13 +150,25 @@ class FlatArena:
 class TrainStep:
     def __init__(self, fbank, normalizer, encoder, decoder, hparams: dict, lr: float = 1e-3,
                  compute_dtype=torch.bfloat16, max_grad_norm: float = 5.0, world_size: int = 1,
-                 seed: int = 123456, overlap_all_reduce: bool = False):
+                 seed: int = 123456, overlap_all_reduce: bool = False, dp_mode: str = "auto"):
+        """``dp_mode`` (world_size > 1): "peer" = gradient reduce-scatter + sharded clip/Adam + parameter all-gather by the two
+        kernels of csrc/dp_optim.cu over NVLink peer memory; "nccl" = one NCCL all-reduce of the flat bucket, then the full
+        Adam on every rank; "auto" = peer when the node's symmetric memory can be set up (all ranks agree), else nccl."""
         self.fbank, self.normalizer, self.encoder, self.decoder = fbank, normalizer, encoder, decoder
         self.hparams = dict(hparams)
         self.dtype = compute_dtype
         self.world_size = world_size
         self.max_grad_norm = max_grad_norm
-        self.arena = FlatArena([encoder, decoder])
+        if dp_mode not in ("auto", "peer", "nccl"):
+            raise ValueError(f"dp_mode must be 'auto', 'peer' or 'nccl', got {dp_mode!r}")
+        peer_alloc = None
+        if world_size > 1 and dp_mode != "nccl" and compute_dtype == torch.bfloat16 and not overlap_all_reduce:
+            from . import peer as _peer
+            peer_alloc = lambda n, dev: _peer.try_peer_memory(n, dev)
+        self.arena = FlatArena([encoder, decoder], peer_memory=peer_alloc)
+        if world_size > 1 and dp_mode == "peer" and self.arena.peer is None:
+            raise RuntimeError("dp_mode='peer': the peer-memory arena could not be set up on this node")
+        self.dp_peer = self.arena.peer is not None
         # optimizer: !name:torch.optim.Adam {lr: 0.001}  (models/test_vanilla_vae/model.yaml:45-47): torch's defaults, run by the
         # fused clip + Adam + zero_grad + bf16-shadow kernel pair of csrc/optim.cu over the flat arena
         self.lr, self.betas, self.eps = lr, (0.9, 0.999), 1e-8
@@ -160,6 +178,12 @@ class TrainStep:
         for m in (encoder, decoder):
             if compute_dtype == torch.bfloat16 and hasattr(m, "bind_arena"):
                 m.bind_arena(self.arena)                       # bf16 shadow weights + gradients accumulated in place
+        if self.dp_peer:
+            self._dp_args = L.DpAdamArgs()
+            self.arena.peer.fill_args(self._dp_args)
+            self._dp_args.exp_avg, self._dp_args.exp_avg_sq = self.arena.exp_avg.data_ptr(), self.arena.exp_avg_sq.data_ptr()
+            self._dp_args.lr, self._dp_args.beta1, self._dp_args.beta2, self._dp_args.eps = lr, self.betas[0], self.betas[1], self.eps
+            self._dp_args.max_grad_norm = float(max_grad_norm or 0.0)
         self.w_kld = loss_weight(self.hparams, "kld_loss")
         self.w_rec = loss_weight(self.hparams, "recon_loss")
         self.epoch = 0
@@ -217,6 +241,18 @@ class TrainStep:
         loss, kld, rec = self.losses(feats, rel)
         self._early_done = False
         loss.backward()
+        lossf = loss.detach().float().reshape(1)
+        a = self.arena
+        if self.dp_peer:
+            # reduce-scatter of the gradients, check_gradients + Adam on this rank's shard, all-gather of the parameters and their bf16
+            # shadow, zero_grad: two launches over the peers' arenas (csrc/dp_optim.cu)
+            args = self._dp_args
+            args.loss = L.ptr(lossf)
+            self._dp_keep = lossf
+            L.check(L.lib().mlvae_dp_adam_step(args, L.stream_ptr()), "mlvae_dp_adam_step", kernels=2)
+            self.step_counter += 1
+            self.last = {"loss": loss.detach(), "kld_loss": kld.detach(), "recon_loss": rec.detach()}
+            return self.last["loss"]
         # gradient SUM over the ranks (the 1 / world_size of the mean is applied inside the optimiser kernel)
         if self.world_size > 1:
             import torch.distributed as dist
@@ -226,8 +262,6 @@ class TrainStep:
             else:
                 dist.all_reduce(self.arena.grad, op=dist.ReduceOp.SUM)
         # check_gradients [SB-recall] (non-finite loss -> skip the update; clip the global norm), Adam, zero_grad, bf16 shadow
-        lossf = loss.detach().float().reshape(1)
-        a = self.arena
         L.check(L.lib().mlvae_adam_clip_step(L.ptr(a.flat), L.ptr(a.grad), L.ptr(a.exp_avg), L.ptr(a.exp_avg_sq), L.ptr(a.flat_bf16), a.flat.numel(),
                                              1.0 / self.world_size, self.lr, self.betas[0], self.betas[1], self.eps, float(self.max_grad_norm or 0.0),
                                              L.ptr(self.adam_state), L.ptr(lossf), L.stream_ptr()), "mlvae_adam_clip_step", kernels=2)
