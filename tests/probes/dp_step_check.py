@@ -16,6 +16,12 @@ from ml_vae_b200.train_step import TrainStep
 B, n, K = 64, 80000, int(os.environ.get("DP_STEPS", 6))
 
 def build(mode):
+    if mode == "local":          # no exchange at all: what one GPU of THIS box does alone (same-box baseline for the scaling loss)
+        torch.manual_seed(123456)
+        fb = Fbank(deltas=True, sample_rate=16000, hop_length=10, n_fft=400, n_mels=80)
+        enc = VanillaVAE([240, 64, 64], 64).to(dev)
+        dec = Decoder(64, 512, 2, 0.15, [1024, 64, 64, 240]).to(dev)
+        return TrainStep(fb, InputNormalization().to(dev), enc, dec, {"kld_weight": 0.001, "batch_size": B}, lr=1e-3, world_size=1)
     torch.manual_seed(123456)
     fb = Fbank(deltas=True, sample_rate=16000, hop_length=10, n_fft=400, n_mels=80)
     enc = VanillaVAE([240, 64, 64], 64).to(dev)
@@ -45,7 +51,8 @@ d = float((pa - pb).abs().max()); rel = d / float(pa.abs().max())
 if rank == 0:
     print(f"max |param_nccl - param_peer| after {K} steps = {d:.3e} (rel {rel:.2e}); loss diff {max(abs(a - b) for a, b in zip(res['nccl'][1], res['peer'][1])):.2e}", flush=True)
 # timing, CUDA-graph replays, both modes on the same box
-for mode in ("nccl", "peer", "nccl", "peer"):
+res["local"] = (None, None, build("local"))
+for mode in ("local", "nccl", "peer", "local", "nccl", "peer"):
     ts = res[mode][2]
     if ts._graph is None:
         ts.capture(wavs[0], lens, warmup=2)
@@ -62,7 +69,7 @@ for mode in ("nccl", "peer", "nccl", "peer"):
         print(f"{mode}: {float(t):.3f} ms/step (graph={ts._graph is not None}, max over ranks, no L2 flush)", flush=True)
 if res["peer"][2].dp_peer:
     print(f"[{rank}] final peer state {res['peer'][2].arena.peer.read_state()}", flush=True)
-for m in res.values():
-    m[2]._graph = None
+for m_ in res.values():
+    m_[2]._graph = None
 dist.barrier(); torch.cuda.synchronize()
 sys.stdout.flush(); os._exit(0)
