@@ -20,7 +20,26 @@ constexpr float kReconEps = 1e-5f;                    // decoder.py:41
 
 template <typename T> __device__ __forceinline__ float fast_exp(float x);
 template <> __device__ __forceinline__ float fast_exp<float>(float x) { return expf(x); }
-template <> __device__ __forceinline__ float fast_exp<__nv_bfloat16>(float x) { return __expf(x); }
+// bf16 kernels: one multiply + MUFU.EX2, flush-to-zero form (no denormal fix-up code around the MUFU: exp underflows to 0 below
+// e^-87 instead of producing denormals, far below anything bf16 can carry)
+__device__ __forceinline__ float ex2_ftz(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+template <> __device__ __forceinline__ float fast_exp<__nv_bfloat16>(float x) { return ex2_ftz(x * 1.4426950408889634f); }
+// exp(x / 2)
+// 1 / x for x >= 1e-5: the bf16 kernels take MUFU.RCP (1 ulp), the float32 kernels the IEEE division
+template <typename T> __device__ __forceinline__ float fast_rcp(float x);
+template <> __device__ __forceinline__ float fast_rcp<float>(float x) { return 1.f / x; }
+template <> __device__ __forceinline__ float fast_rcp<__nv_bfloat16>(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+template <typename T> __device__ __forceinline__ float exp_half(float x);
+template <> __device__ __forceinline__ float exp_half<float>(float x) { return expf(0.5f * x); }
+template <> __device__ __forceinline__ float exp_half<__nv_bfloat16>(float x) { return ex2_ftz(x * 0.7213475204444817f); }
 
 // ---------------------------------------------------------------------------
 // Walks the (rows x C) matrix in units of VEC contiguous elements of one row.
@@ -201,9 +220,8 @@ template <typename T, int VEC> struct Chunk {   // VEC == Vec<T>::N (vector path
 template <typename T, int VEC>
 __global__ void __launch_bounds__(kThreads)
 reparam_kl_fwd_kernel(const T *__restrict__ mu, const T *__restrict__ logvar, const T *__restrict__ eps,
-                      uint64_t seed, uint64_t offset, const uint64_t *__restrict__ offset_add, const float *__restrict__ lens, int B, int Tn, int L,
+                      const PhiloxKey key, uint64_t offset, const uint64_t *__restrict__ offset_add, const float *__restrict__ lens, int B, int Tn, int L,
                       T *__restrict__ z, T *__restrict__ kl_elem, float *__restrict__ kl_out, ReduceScratch *scratch) {
-    const PhiloxKey key(seed);
     if (offset_add) offset += __ldg(offset_add);      // device-resident step counter (CUDA-graph friendly)
     float acc = 0.f;
     for (RowWalker w((int64_t)B * Tn, L / VEC, Tn); w.valid(); w.next()) {
@@ -218,11 +236,13 @@ reparam_kl_fwd_kernel(const T *__restrict__ mu, const T *__restrict__ logvar, co
         float part = 0.f;
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
-            const float sd = fast_exp<T>(0.5f * lv.v[i]);
+            const float sd = exp_half<T>(lv.v[i]);
             zz.v[i] = fmaf(ep.v[i], sd, m.v[i]);
-            const float k = -0.5f * (1.f + lv.v[i] - m.v[i] * m.v[i] - sd * sd);
+            float k;
+            if constexpr (sizeof(T) == 2) k = fmaf(0.5f, fmaf(m.v[i], m.v[i], sd * sd), fmaf(-0.5f, lv.v[i], -0.5f));    // same value, 4 instructions
+            else k = -0.5f * (1.f + lv.v[i] - m.v[i] * m.v[i] - sd * sd);
             kk.v[i] = k;
-            part += k * maskf;      // multiply, not select: inf*0 = NaN like loss*mask in the reference
+            part = fmaf(k, maskf, part);      // multiply, not select: inf*0 = NaN like loss*mask in the reference
         }
         acc += part;
         zz.store(z + e0);
@@ -234,11 +254,10 @@ reparam_kl_fwd_kernel(const T *__restrict__ mu, const T *__restrict__ logvar, co
 template <typename T, int VEC>
 __global__ void __launch_bounds__(kThreads)
 reparam_kl_bwd_kernel(const T *__restrict__ mu, const T *__restrict__ logvar, const T *__restrict__ eps,
-                      uint64_t seed, uint64_t offset, const uint64_t *__restrict__ offset_add, const T *__restrict__ grad_z,
+                      const PhiloxKey key, uint64_t offset, const uint64_t *__restrict__ offset_add, const T *__restrict__ grad_z,
                       const T *__restrict__ grad_kl_elem, const float *__restrict__ grad_kl_mean,
                       const float *__restrict__ lens, int B, int Tn, int L,
                       T *__restrict__ grad_mu, T *__restrict__ grad_logvar) {
-    const PhiloxKey key(seed);
     if (offset_add) offset += __ldg(offset_add);
     const float gscale = mean_grad_scale(grad_kl_mean, lens, B, Tn, L);
     for (RowWalker w((int64_t)B * Tn, L / VEC, Tn); w.valid(); w.next()) {
@@ -254,7 +273,7 @@ reparam_kl_bwd_kernel(const T *__restrict__ mu, const T *__restrict__ logvar, co
         if (grad_kl_mean) gm_row = gscale * (((float)w.t < mask_threshold(__ldg(lens + w.b), Tn)) ? 1.f : 0.f);
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
-            const float sd = fast_exp<T>(0.5f * lv.v[i]);
+            const float sd = exp_half<T>(lv.v[i]);
             const float g = ge.v[i] + gm_row;
             gm.v[i] = fmaf(g, m.v[i], gz.v[i]);
             gl.v[i] = fmaf(gz.v[i] * 0.5f * sd, ep.v[i], g * 0.5f * (sd * sd - 1.f));
@@ -285,9 +304,10 @@ recon_fwd_kernel(const T *__restrict__ mean, const T *__restrict__ logvar, const
             const float d = tg.v[i] - m.v[i];
             float l;
             if constexpr (kMse) l = d * d;
+            else if constexpr (sizeof(T) == 2) l = 0.5f * (kLog2Pi_f32 + lv.v[i] + d * d * fast_rcp<T>(fast_exp<T>(lv.v[i]) + kReconEps));
             else l = 0.5f * (kLog2Pi_f32 + lv.v[i] + d * d / (fast_exp<T>(lv.v[i]) + kReconEps));
             ll.v[i] = l;
-            part += l * maskf;
+            part = fmaf(l, maskf, part);
         }
         acc += part;
         if (elem) ll.store(elem + e0);
@@ -320,7 +340,7 @@ recon_bwd_kernel(const T *__restrict__ mean, const T *__restrict__ logvar, const
                 gm.v[i] = -gt.v[i];
             } else {
                 const float e = fast_exp<T>(lv.v[i]);
-                const float inv = 1.f / (e + kReconEps);
+                const float inv = fast_rcp<T>(e + kReconEps);
                 gt.v[i] = g * d * inv;                       // d/dtarget = (t-m)/(e+eps)
                 gm.v[i] = -gt.v[i];
                 gl.v[i] = g * 0.5f * (1.f - d * d * e * inv * inv);
@@ -423,7 +443,7 @@ gmm_reparam_kl_fwd_kernel(const T *__restrict__ mu, const T *__restrict__ logvar
         else stream_eps<T, VEC>(e0, offset, key, ep.v);
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
-            const float sd = fast_exp<T>(0.5f * lv.v[i]);
+            const float sd = exp_half<T>(lv.v[i]);
             zz.v[i] = fmaf(ep.v[i], sd, m.v[i]);
             const float d = m.v[i] - pm.v[i];
             kk.v[i] = -0.5f * (1.f + lv.v[i] - plv.v[i] - (sd * sd + d * d) / (fast_exp<T>(plv.v[i]) + kGmmEps));
@@ -452,7 +472,7 @@ gmm_reparam_kl_bwd_kernel(const T *__restrict__ mu, const T *__restrict__ logvar
         else stream_eps<T, VEC>(e0, offset, key, ep.v);
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
-            const float sd = fast_exp<T>(0.5f * lv.v[i]);
+            const float sd = exp_half<T>(lv.v[i]);
             const float e = sd * sd, ep_ = fast_exp<T>(plv.v[i]);
             const float inv = 1.f / (ep_ + kGmmEps);
             const float d = m.v[i] - pm.v[i];
@@ -661,7 +681,7 @@ int mlvae_reparam_kl_fwd(const void *d_mu, const void *d_logvar, const void *d_e
     MLVAE_DISPATCH(dtype, L, al, {
         const int64_t nvec = (int64_t)B * T_ * (L / VEC);
         reparam_kl_fwd_kernel<T, VEC><<<grid_for(nvec), kThreads, 0, (cudaStream_t)stream>>>(
-            (const T *)d_mu, (const T *)d_logvar, (const T *)d_eps, seed, offset, d_offset_add, d_lens, B, T_, L, (T *)d_z,
+            (const T *)d_mu, (const T *)d_logvar, (const T *)d_eps, PhiloxKey(seed), offset, d_offset_add, d_lens, B, T_, L, (T *)d_z,
             (T *)d_kl_elem, d_kl_out, (ReduceScratch *)d_scratch);
     });
     MLVAE_CHECK_CUDA(cudaGetLastError());
@@ -680,7 +700,7 @@ int mlvae_reparam_kl_bwd(const void *d_mu, const void *d_logvar, const void *d_e
     MLVAE_DISPATCH(dtype, L, al, {
         const int64_t nvec = (int64_t)B * T_ * (L / VEC);
         reparam_kl_bwd_kernel<T, VEC><<<grid_for(nvec), kThreads, 0, (cudaStream_t)stream>>>(
-            (const T *)d_mu, (const T *)d_logvar, (const T *)d_eps, seed, offset, d_offset_add, (const T *)d_grad_z,
+            (const T *)d_mu, (const T *)d_logvar, (const T *)d_eps, PhiloxKey(seed), offset, d_offset_add, (const T *)d_grad_z,
             (const T *)d_grad_kl_elem, d_grad_kl_mean, d_lens, B, T_, L, (T *)d_grad_mu, (T *)d_grad_logvar);
     });
     MLVAE_CHECK_CUDA(cudaGetLastError());

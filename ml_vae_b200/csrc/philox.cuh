@@ -6,8 +6,10 @@
 namespace mlvae {
 
 struct PhiloxKey {
-    uint32_t k0[10], k1[10];   // per-round keys, precomputed once per thread
-    __device__ __forceinline__ explicit PhiloxKey(uint64_t seed) {
+    uint32_t k0[10], k1[10];   // per-round keys; built on the HOST and passed by value where the kernel is issue bound (the
+                               // rounds then take them straight from the constant bank: a key derived from a `seed` parameter is
+                               // re-derived in uniform registers on every loop iteration, 18 issue slots per Philox call)
+    __host__ __device__ __forceinline__ explicit PhiloxKey(uint64_t seed) {
         uint32_t a = (uint32_t)seed, b = (uint32_t)(seed >> 32);
 #pragma unroll
         for (int r = 0; r < 10; ++r) {
@@ -61,8 +63,10 @@ __device__ __forceinline__ void philox_normal4(uint64_t q, uint64_t offset, cons
 __device__ __forceinline__ void box_muller16(uint32_t w, float &n0, float &n1) {
     const float u1 = __uint2float_rn((w & 0xffffu) + 1u) * 1.52587890625e-05f;
     const float th = __int2float_rn((int)(w >> 16) - 32768) * 9.587379924285257e-05f;
-    float r;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-2.0f * __logf(u1)));
+    // -2 ln u1 = (-2 ln 2) lg2 u1; u1 >= 2^-16 is never denormal: the .ftz forms skip the range fix-ups (3 instructions each)
+    float l2, r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(u1));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-1.3862943611198906f * l2));
     float s, c;
     __sincosf(th, &s, &c);
     n0 = r * c;
