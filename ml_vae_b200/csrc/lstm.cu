@@ -103,8 +103,14 @@ __device__ long long *g_prof = nullptr;     // optional per-phase cycle counters
     } while (0)
 #define PROF_FLUSH()                                                     \
     do {                                                                 \
-        if constexpr (kProf) { if (prof) { for (int k_ = 0; k_ < 4; ++k_) prof[k_] += pacc[k_]; } } \
+        if constexpr (kProf) { if (prof) { for (int k_ = 0; k_ < 4; ++k_) { prof[k_] += pacc[k_]; if (prof2) prof2[k_] += pacc[k_]; } } } \
     } while (0)
+// profile buffer layout (int64, 128 entries): [0..3] gate warp 0 of chain 0 of CTA (0,0,0), [4..11] its issuer warps, [12 + 4 x ..] gate
+// warp 0 of chain 0 of CTA (x,0,0) for every x (is one CTA of the group the slow one?), [76 + 4 w ..] gate warp w of chain 0 of CTA (0,0,0)
+#define PROF_SETUP()                                                                                                                     \
+    const bool prof_on = kProf && g_prof && blockIdx.y == 0 && blockIdx.z == 0 && chain == 0 && lane == 0 && (warp == 0 || blockIdx.x == 0); \
+    long long *prof = !prof_on ? nullptr : (warp == 0 ? (blockIdx.x == 0 ? g_prof : g_prof + 12 + 4 * blockIdx.x) : g_prof + 76 + 4 * warp); \
+    long long *prof2 = (prof_on && warp == 0 && blockIdx.x == 0) ? g_prof + 12 : nullptr
 
 struct LstmFwdParams {
     bf16 *P;                 // (B, T, 2, H, 4) gate pre-activations (unit-major, the 4 gates i,f,g,o adjacent) from the input projection;
@@ -261,7 +267,7 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_fwd_kernel(LstmFwdParams
         // on the DRAM latency inside the step)
         uint2 pre_raw = *pG;
 
-        long long *prof = !kProf ? nullptr : ((g_prof && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && warp == 0 && lane == 0) ? g_prof : nullptr);
+        PROF_SETUP();
         long long tprev = clock64(), pacc[4] = {0, 0, 0, 0};
 
         long long t_pub = 0;
@@ -535,7 +541,7 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_bwd_kernel(LstmBwdParams
         float rc = p.C[y_off];
         float rcp = (T > 1) ? p.C[y_off + y_step] : 0.f;          // c_{t-1} in forward order == next time index visited here
 
-        long long *prof = !kProf ? nullptr : ((g_prof && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && warp == 0 && lane == 0) ? g_prof : nullptr);
+        PROF_SETUP();
         long long tprev = clock64(), pacc[4] = {0, 0, 0, 0};
 
         long long t_pub = 0;
@@ -702,8 +708,7 @@ int lstm_plan(int B, int H, LstmPlan &pl) {
 
 extern "C" {
 
-// Debug: d_prof = 8 zeroed int64 cycle counters filled by gate warp 0 ([0..3]) and the issuer warp ([4..7]) of chain 0 of CTA (0,0,0) by the
-// next LSTM launches; NULL disables.
+// Debug: d_prof = 128 zeroed int64 cycle counters (layout at PROF_SETUP) filled by the next LSTM launches; NULL disables.
 int mlvae_debug_set_profile_buffer(void *d_prof) {
     long long *ptr = (long long *)d_prof;
     MLVAE_CHECK_CUDA(cudaMemcpyToSymbol(g_prof, &ptr, sizeof(ptr)));

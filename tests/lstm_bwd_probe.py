@@ -49,12 +49,19 @@ def run(B, T, In, H, time_it=False):
         for _ in range(3): step()
         b.record(); torch.cuda.synchronize()
         ours = a.elapsed_time(b) / 3
-        prof = torch.zeros(8, dtype=torch.int64, device=dev)
+        prof = torch.zeros(128, dtype=torch.int64, device=dev)
         yy = bilstm_layer(xm, *ps, training=True)
         L.check(L.lib().mlvae_debug_set_profile_buffer(L.ptr(prof)), "prof")
         yy.backward(gy); torch.cuda.synchronize()
         L.check(L.lib().mlvae_debug_set_profile_buffer(None), "prof")
         print("   bwd cycles/step:", dict(zip(["exchange wait", "reduce", "gate grads + hand-off", "mma completion + scatter", "issuer 0: wait dA", "issuer 0: issue + commit", "issuer 1: wait dA", "issuer 1: issue + commit"], [round(v / T) for v in prof.cpu().tolist()[:8]])))
+        pc = prof.cpu().tolist()
+        print("   per CTA of group 0 (gate warp 0, chain 0) [wait, reduce, gates, mma+scatter]:")
+        for x in range(H // 32):
+            print("     cta", x, [round(v / T) for v in pc[12 + 4 * x: 16 + 4 * x]])
+        print("   per gate warp of CTA 0 chain 0:")
+        for w in range(1, 8):
+            print("     warp", w, [round(v / T) for v in pc[76 + 4 * w: 80 + 4 * w]])
         lb = ref.bfloat16()
         def rstep():
             xb = x.clone().requires_grad_(True)
@@ -68,6 +75,10 @@ def run(B, T, In, H, time_it=False):
     return worst < 3e-2
 
 
+import sys
+if len(sys.argv) > 1:                      # python tests/lstm_bwd_probe.py B T  -> instrumented timing of that shape only
+    run(int(sys.argv[1]), int(sys.argv[2]), 64, 512, time_it=True)
+    sys.exit(0)
 ok = True
 ok &= run(4, 6, 16, 32)
 ok &= run(16, 20, 24, 64)

@@ -34,7 +34,7 @@ def run(B, T, In, H, time_it=False):
     cerr = float((C[:, -1, :H] - cn[0]).abs().max() / cn[0].abs().max())
     print(f"B={B} T={T} In={In} H={H}: y rel err {err:.3e}  c_T rel err {cerr:.3e}", "OK" if err < 2e-2 else "MISMATCH", flush=True)
     if time_it:
-        prof = torch.zeros(8, dtype=torch.int64, device=dev)
+        prof = torch.zeros(128, dtype=torch.int64, device=dev)
         L.check(L.lib().mlvae_debug_set_profile_buffer(L.ptr(prof)), "prof")
         L.check(L.lib().mlvae_lstm_fwd(L.ptr(P), L.ptr(whh), L.ptr(Y), L.ptr(C), B, T, H, 1, L.ptr(scratch), L.stream_ptr()), "lstm_fwd")
         torch.cuda.synchronize()
@@ -43,6 +43,12 @@ def run(B, T, In, H, time_it=False):
                  "issuer 0: wait", "issuer 0: issue + commit", "issuer 1: wait", "issuer 1: issue + commit"]
         pc = prof.cpu().tolist()
         print("   cycles/step:", {n: round(v / T) for n, v in zip(names, pc)}, "total", round(sum(pc[:4]) / T))
+        print("   per CTA of group 0 (gate warp 0, chain 0) [wait, B tile, mma, gates]:")
+        for x in range(H // 32):
+            print("     cta", x, [round(v / T) for v in pc[12 + 4 * x: 16 + 4 * x]])
+        print("   per gate warp of CTA 0 chain 0:")
+        for w in range(1, 8):
+            print("     warp", w, [round(v / T) for v in pc[76 + 4 * w: 80 + 4 * w]])
         for sv in (0, 1):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
@@ -64,6 +70,10 @@ def run(B, T, In, H, time_it=False):
     return err < 2e-2
 
 
+import sys
+if len(sys.argv) > 1:                      # python tests/lstm_probe.py B T  -> instrumented timing of that shape only
+    run(int(sys.argv[1]), int(sys.argv[2]), 64, 512, time_it=True)
+    sys.exit(0)
 ok = True
 ok &= run(4, 6, 16, 32)
 ok &= run(16, 20, 24, 64)

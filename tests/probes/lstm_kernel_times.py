@@ -7,7 +7,7 @@ L.LIB_PATH = os.environ.get('AB_LIB', L.LIB_PATH)      # A/B against another bui
 from ml_vae_b200.lstm import _gate_perm
 
 dev = torch.device("cuda:0")
-B, T, H, In = 64, 500, 512, 64
+B, T, H, In = int(os.environ.get("LSTM_B", 64)), 500, 512, 64
 torch.manual_seed(1)
 lstm = torch.nn.LSTM(In, H, 1, bidirectional=True, batch_first=True).to(dev)
 x = torch.randn(B, T, In, device=dev)
@@ -21,7 +21,7 @@ whh = torch.stack([lstm.weight_hh_l0, lstm.weight_hh_l0_reverse], 0).bfloat16().
 Y = torch.empty(B, T, 2 * H, device=dev, dtype=torch.bfloat16)
 C = torch.empty(B, T, 2 * H, device=dev)
 dY = torch.randn(B, T, 2 * H, device=dev).bfloat16()
-db = torch.empty(4, 2, 4 * H, device=dev)
+db = torch.empty((B + 15) // 16, 2, 4 * H, device=dev)
 scratch = torch.empty(L.lib().mlvae_lstm_scratch_bytes(B, H), dtype=torch.uint8, device=dev)
 lib = L.lib()
 
