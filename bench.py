@@ -268,7 +268,8 @@ def run_ours(args):
     dec = Decoder(W["latent"], W["rnn_hidden"], W["rnn_layers"], W["rnn_dropout"],
                   [2 * W["rnn_hidden"], W["dec_fc"], W["dec_fc"], D]).to(dev)
     ts = TrainStep(fb, InputNormalization().to(dev), enc, dec, {"kld_weight": 0.001, "batch_size": B}, lr=1e-3,
-                   compute_dtype=dtype, world_size=world, overlap_all_reduce=args.overlap, dp_mode=args.dp_mode)
+                   compute_dtype=dtype, world_size=world, overlap_all_reduce=args.overlap, dp_mode=args.dp_mode,
+                   defer_weight_grads=not args.no_defer)
 
     g = torch.Generator().manual_seed(123456 + rank)
     R = 4                                                       # distinct resident batches, rotated
@@ -514,6 +515,7 @@ def main():
     ap.add_argument("--dp-mode", default="auto", choices=["auto", "peer", "nccl"],
                     help="N > 1: peer = reduce-scatter + sharded Adam + all-gather kernels over NVLink peer memory (csrc/dp_optim.cu), "
                          "nccl = NCCL all-reduce + full Adam on every rank, auto = peer when the node's symmetric memory is available")
+    ap.add_argument("--no-defer", action="store_true", help="A/B: run the upper LSTM layer's weight-gradient GEMMs in line instead of beside the lower layer's recurrence")
     ap.add_argument("--overlap", action="store_true", help="all-reduce the tail of the gradient bucket under the first LSTM layer's backward (measured slower at N=2)")
     args = ap.parse_args()
     global WORKLOAD

@@ -311,6 +311,8 @@ int mlvae_dp_debug_max_ctas(int n);          /* tests: cap both grids so that se
  *   split_k > 1: the reduction is cut in split_k parts whose float32 partials go to ws
  *      (mlvae_gemm_workspace_bytes) and are added in split order by a second kernel (deterministic); f32 output only.
  *   bn: N tile (64, 128, 256; 0 = chosen from N).  N, lda, ldb %% 8 == 0; all pointers 16-byte aligned.
+ *   max_ctas: cap of the persistent grid (0 = one CTA per SM): a GEMM that runs on a side stream BESIDE the persistent LSTM
+ *      recurrence is confined to the SMs that launch leaves idle (lstm.py: the upper layer's dW_hh under the lower layer's backward).
  * ------------------------------------------------------------------------- */
 #define MLVAE_GEMM_MAX_PROBLEMS 4
 typedef struct mlvae_gemm_args {
@@ -329,6 +331,7 @@ typedef struct mlvae_gemm_args {
     uint64_t drop_seed, drop_offset;
     const void *drop_offset_add; /* device uint64[1] added to drop_offset, or NULL */
     int bn;
+    int max_ctas;                /* > 0: at most this many (persistent) CTAs, e.g. the SMs a concurrently running cooperative kernel leaves idle */
 } mlvae_gemm_args;
 size_t mlvae_gemm_workspace_bytes(int nprob, int M, int N, int split_k);
 int mlvae_gemm_bf16(const mlvae_gemm_args *args, void *stream);

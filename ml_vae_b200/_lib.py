@@ -26,7 +26,7 @@ class GemmArgs(C.Structure):
                 ("M", _i), ("N", _i), ("K", _i), ("kbatches", _i), ("a_mn_major", _i), ("b_mn_major", _i),
                 ("lda", _i64), ("ldb", _i64), ("a_batch_stride", _i64), ("b_batch_stride", _i64), ("ldd", _i64),
                 ("out_f32", _i), ("accumulate", _i), ("leaky", _i), ("row_perm_H", _i), ("split_k", _i), ("ws", _vp),
-                ("drop_p", C.c_float), ("drop_seed", _u64), ("drop_offset", _u64), ("drop_offset_add", _vp), ("bn", _i)]
+                ("drop_p", C.c_float), ("drop_seed", _u64), ("drop_offset", _u64), ("drop_offset_add", _vp), ("bn", _i), ("max_ctas", _i)]
 
 
 class ChainFwdArgs(C.Structure):

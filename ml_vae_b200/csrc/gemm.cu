@@ -450,7 +450,8 @@ int mlvae_gemm_bf16(const mlvae_gemm_args *a, void *stream) {
     }
     const int total = prm.nprob * split * prm.tiles_m * prm.tiles_n;
     const int sms = sm_count();
-    const int grid = total < sms ? total : sms;
+    int grid = total < sms ? total : sms;
+    if (a->max_ctas > 0 && a->max_ctas < grid) grid = a->max_ctas;
     cudaStream_t st = (cudaStream_t)stream;
     int rc = bn == 256 ? launch_gemm<256>(prm, grid, st) : bn == 128 ? launch_gemm<128>(prm, grid, st) : launch_gemm<64>(prm, grid, st);
     if (rc) return rc;

@@ -29,7 +29,7 @@ def _workspace(nbytes: int, device):
 def gemm(A, B, D, M: int, N: int, K: int, *, lda: int, ldb: int, ldd: int, a_mn: bool = False, b_mn: bool = False,
          kbatches: int = 1, a_batch_stride: int = 0, b_batch_stride: int = 0, bias=None, out_f32: bool = False,
          accumulate: bool = False, leaky: bool = False, row_perm_H: int = 0, split_k: int = 1, drop_p: float = 0.0,
-         drop_seed: int = 0, drop_offset: int = 0, drop_offset_dev=None, bn: int = 0):
+         drop_seed: int = 0, drop_offset: int = 0, drop_offset_dev=None, bn: int = 0, max_ctas: int = 0):
     """D_i (+)= epilogue(A_i B_i) for the problems i of the lists A, B, D (single tensors are wrapped).  See
     include/mlvae_b200.h for the operand conventions (K-major / MN-major, batched reduction, epilogue)."""
     As, Bs, Ds = (list(t) if isinstance(t, (list, tuple)) else [t] for t in (A, B, D))
@@ -53,6 +53,7 @@ def gemm(A, B, D, M: int, N: int, K: int, *, lda: int, ldb: int, ldd: int, a_mn:
     a.drop_p, a.drop_seed, a.drop_offset = float(drop_p), drop_seed, drop_offset
     a.drop_offset_add = None if drop_offset_dev is None else drop_offset_dev.data_ptr()
     a.bn = bn
+    a.max_ctas = max_ctas
     ev0 = None
     if PROBE is not None:
         ev0 = torch.cuda.Event(enable_timing=True)

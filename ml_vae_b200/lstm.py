@@ -15,6 +15,36 @@ from . import _lib as L
 _scratch = {}
 PROBE = None      # bench.py sets this to a list; every recurrence launch then appends (tag, start_event, end_event)
 
+# Weight-gradient GEMMs of an UPPER layer that its backward left for the next recurrence launch to hide.  The persistent
+# recurrence is a cooperative launch of 2 * (H / 32) * ceil(B / 16) CTAs, one per SM (128 of 148 at the benchmark shape, 32 at
+# configs[3]) that spends its time waiting on the inter-CTA exchange; the SMs it does not use are idle for ~1 ms.  A layer whose
+# ``defer_weight_grads`` is set therefore only QUEUES its dW GEMMs; the backward of the layer below launches them on a side
+# stream, confined to the idle SMs (gemm(max_ctas=...)), right before its own recurrence, and joins the streams after it.
+_DEFERRED = []
+_SIDE = {}
+
+
+def _side_stream(device):
+    key = torch.device(device).index
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device)
+    return _SIDE[key]
+
+
+def idle_sms(B: int, hidden: int, device) -> int:
+    """SMs the recurrence launch for (B rows, hidden) leaves idle."""
+    sms = torch.cuda.get_device_properties(device).multi_processor_count
+    rows = min(B, max_rows_per_launch(hidden, device))
+    return max(0, sms - 2 * (hidden // 32) * ((rows + 15) // 16))
+
+
+def flush_deferred():
+    """Run whatever weight-gradient GEMMs are still queued on the current stream (no recurrence left to hide them under)."""
+    work = _DEFERRED[:]
+    _DEFERRED.clear()
+    for w in work:
+        w(0)
+
 
 def max_rows_per_launch(hidden: int, device) -> int:
     """Batch rows one cooperative launch can take: every (direction, 16-row slice, 32-unit slice) CTA must be
@@ -103,7 +133,7 @@ class _BiLSTMLayer(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r, training, direct_grads, after_recurrence,
-                input_dropout):
+                input_dropout, defer_weight_grads=False):
         """x (B,T,In) bf16 -> y (B,T,2H) bf16.  ``input_dropout`` = (p, seed, offset, offset_dev) or None: the layer's input is
         dropout(x) with the counter-based mask of csrc/dropout.cu (the inter-layer dropout of nn.LSTM, decoder.py:14-15)."""
         from .gemm import gemm
@@ -133,6 +163,7 @@ class _BiLSTMLayer(torch.autograd.Function):
         ctx.masters = masters if (training and direct_grads) else None
         ctx.after_recurrence = after_recurrence
         ctx.input_dropout = input_dropout
+        ctx.defer_weight_grads = bool(defer_weight_grads)
         ctx.use_gemm = _gemm_ok(In, H, x2)
         if ctx.use_gemm:
             P = torch.empty(B, T, 2, 4 * H, dtype=bf, device=x.device)
@@ -173,12 +204,25 @@ class _BiLSTMLayer(torch.autograd.Function):
         n_slices = sum((min(B, b0 + rows) - b0 + 15) // 16 for b0 in range(0, B, rows))
         db_part = torch.empty(n_slices, 8 * H, dtype=torch.float32, device=dev)
         part0 = 0
+        # weight-gradient GEMMs the layer above queued: on a side stream, on the SMs this recurrence leaves idle
+        beside, side = _DEFERRED[:], None
+        _DEFERRED.clear()
+        if beside:
+            main, side = torch.cuda.current_stream(dev), _side_stream(dev)
+            side.wait_stream(main)
+            free = idle_sms(B, H, dev)
+            with torch.cuda.stream(side):
+                for w in beside:
+                    w(free)
         for b0 in range(0, B, rows):
             b1 = min(B, b0 + rows)
             L.check(L.lib().mlvae_lstm_bwd(L.ptr(gates[b0:b1]), L.ptr(c[b0:b1]), L.ptr(dy[b0:b1]), L.ptr(w_hh), L.ptr(db_part[part0:]),
                                            b1 - b0, T, H, L.ptr(_get_scratch(b1 - b0, H, dev)), L.stream_ptr()), "mlvae_lstm_bwd")
             part0 += (b1 - b0 + 15) // 16
         _probe_end("lstm_bwd", ev)
+        if beside:
+            torch.cuda.current_stream(dev).wait_stream(side)               # their operands are released only after this join
+            del beside
         if ctx.after_recurrence is not None:
             ctx.after_recurrence()                                         # e.g. start the all-reduce of the layers above
         dA = gates                                                         # now pre-activation gradients (B,T,2,H,4)
@@ -209,22 +253,39 @@ class _BiLSTMLayer(torch.autograd.Function):
             g_hh = [torch.zeros(H4, H, dtype=torch.float32, device=dev) for _ in range(2)]
             g_b = [torch.zeros(H4, dtype=torch.float32, device=dev) for _ in range(4)]
         # dW_ih[d] = dA[:, d]^T x: both operands MN-major; few output tiles for a narrow input -> split the B*T reduction
-        tiles = 2 * ((H4 + 127) // 128) * ((In + 255) // 256)
-        split = 1 if tiles >= 96 else max(1, min(8, 128 // tiles))
-        gemm([dA2[:, :H4], dA2[:, H4:]], [x2, x2], g_ih, H4, In, B * T, lda=8 * H, ldb=In, ldd=In, a_mn=True, b_mn=True, out_f32=True,
-             accumulate=direct, row_perm_H=H, split_k=split)
-        if T > 1:
+        # With ``defer_weight_grads`` (and gradients accumulated in place) the products are only queued: the backward of the layer
+        # below runs them beside its recurrence on the SMs that launch leaves idle (dW_hh always; dW_ih too when most SMs are idle).
+        free = idle_sms(B, H, dev) if (ctx.defer_weight_grads and direct) else 0
+
+        def dw_ih(max_ctas=0):
+            tiles = 2 * ((H4 + 127) // 128) * ((In + 255) // 256)
+            split = 1 if tiles >= 96 else max(1, min(8, 128 // tiles))
+            gemm([dA2[:, :H4], dA2[:, H4:]], [x2, x2], g_ih, H4, In, B * T, lda=8 * H, ldb=In, ldd=In, a_mn=True, b_mn=True, out_f32=True,
+                 accumulate=direct, row_perm_H=H, split_k=split, max_ctas=max_ctas)
+
+        def dw_hh(max_ctas=0):
             # dW_hh[d] = sum_b sum_t dA[b,t,d]^T h_prev[b,t,d], h_prev the previous step IN THAT DIRECTION'S ORDER (forward: y[b,t-1,:H];
             # reverse: y[b,t+1,H:]): a batched reduction over row-shifted views, T-1 rows per utterance (TMA zero-fills past them)
             tiles = 2 * ((H4 + 127) // 128) * ((H + 255) // 256)
             split = 1 if tiles >= 96 else max(1, min(4, 128 // tiles))
             gemm([dA2[1:, :H4], dA2[:, H4:]], [y2[:, :H], y2[1:, H:]], g_hh, H4, H, T - 1, lda=8 * H, ldb=2 * H, ldd=H, a_mn=True, b_mn=True,
-                 kbatches=B, a_batch_stride=T * 8 * H, b_batch_stride=T * 2 * H, out_f32=True, accumulate=direct, row_perm_H=H, split_k=split)
+                 kbatches=B, a_batch_stride=T * 8 * H, b_batch_stride=T * 2 * H, out_f32=True, accumulate=direct, row_perm_H=H, split_k=split,
+                 max_ctas=max_ctas)
+
+        if free >= 64:
+            _DEFERRED.append(dw_ih)
+        else:
+            dw_ih()
+        if T > 1:
+            if free >= 16:
+                _DEFERRED.append(dw_hh)
+            else:
+                dw_hh()
         L.check(L.lib().mlvae_lstm_bias_grads(L.ptr(db_part), n_slices, H, L.ptr(g_b[0]), L.ptr(g_b[1]), L.ptr(g_b[2]), L.ptr(g_b[3]), L.stream_ptr()),
                 "mlvae_lstm_bias_grads")
         if direct:
-            return (dx,) + (None,) * 12
-        return dx, g_ih[0], g_hh[0], g_b[0], g_b[1], g_ih[1], g_hh[1], g_b[2], g_b[3], None, None, None, None
+            return (dx,) + (None,) * 13
+        return dx, g_ih[0], g_hh[0], g_b[0], g_b[1], g_ih[1], g_hh[1], g_b[2], g_b[3], None, None, None, None, None
 
     @staticmethod
     def _backward_library(ctx, dA, dA2, x2, y, y2, w_ih_p, db_part, masters, B, T, In, H):
@@ -255,17 +316,20 @@ class _BiLSTMLayer(torch.autograd.Function):
         if masters is not None:
             for m, g in zip(masters, grads):
                 m.grad.add_(g)
-            return (dx,) + (None,) * 12
-        return (dx, *grads, None, None, None, None)
+            return (dx,) + (None,) * 13
+        return (dx, *grads, None, None, None, None, None)
 
 
 def bilstm_layer(x, w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r, training: bool, direct_grads: bool = False,
-                 after_recurrence=None, input_dropout=None):
+                 after_recurrence=None, input_dropout=None, defer_weight_grads: bool = False):
     """One bidirectional layer with torch's per-direction parameters (float32 masters; cast inside the layer).
     ``direct_grads``: accumulate the parameter gradients straight into the parameters' existing float32 ``.grad``
     buffers (valid under ``loss.backward()``; the training step that owns a flat gradient bucket turns it on).
     ``after_recurrence``: callable run in backward right after the recurrence kernel is enqueued, before the layer's
     weight-gradient GEMMs.  ``input_dropout`` = (p, seed, offset, offset_dev): the layer consumes dropout(x) (counter-based
-    mask, csrc/dropout.cu); the mask of the backward pass is applied inside the input-gradient GEMM."""
+    mask, csrc/dropout.cu); the mask of the backward pass is applied inside the input-gradient GEMM.
+    ``defer_weight_grads`` (needs ``direct_grads``): backward only queues the layer's weight-gradient GEMMs; the backward of the
+    NEXT bilstm_layer runs them beside its recurrence on the idle SMs, ``flush_deferred()`` runs whatever is left -- the caller
+    guarantees one of the two happens before the gradients are read (Decoder: every layer but the lowest; TrainStep flushes)."""
     return _BiLSTMLayer.apply(x.contiguous(), w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r, training,
-                              direct_grads, after_recurrence, input_dropout)
+                              direct_grads, after_recurrence, input_dropout, defer_weight_grads)

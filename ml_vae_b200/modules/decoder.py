@@ -38,6 +38,7 @@ class Decoder(nn.Module):
         self.dropout_calls = 0
         self.dropout_offset_dev = None
         self.direct_param_grads = False       # train_step.py: LSTM gradients accumulate straight into the flat bucket
+        self.defer_weight_grads = False       # train_step.py: upper layers' dW GEMMs run beside the recurrence of the layer below
         self.top_layer_grad_hook = None      # callable(): runs in backward once the top LSTM layer's and the heads' gradients exist
         self._rnn_names = []
         for name, p in torch_default_lstm(self.input_size, self.hidden, self.num_layers):
@@ -91,7 +92,7 @@ class Decoder(nn.Module):
                 if self.rnn_dropout > 0 and self.training and layer > 0:
                     drop = (self.rnn_dropout, self.dropout_seed, self._dropout_offset(layer - 1), self.dropout_offset_dev)
                 x = lstm.bilstm_layer(x, *ps, training=need_grad, direct_grads=self.direct_param_grads, after_recurrence=hook,
-                                      input_dropout=drop)
+                                      input_dropout=drop, defer_weight_grads=self.defer_weight_grads and layer > 0)
             if self.rnn_dropout > 0 and self.training:
                 self.dropout_calls += 1
             return x

@@ -150,7 +150,8 @@ class FlatArena:
 class TrainStep:
     def __init__(self, fbank, normalizer, encoder, decoder, hparams: dict, lr: float = 1e-3,
                  compute_dtype=torch.bfloat16, max_grad_norm: float = 5.0, world_size: int = 1,
-                 seed: int = 123456, overlap_all_reduce: bool = False, dp_mode: str = "auto"):
+                 seed: int = 123456, overlap_all_reduce: bool = False, dp_mode: str = "auto",
+                 defer_weight_grads: bool = True):
         """``dp_mode`` (world_size > 1): "peer" = gradient reduce-scatter + sharded clip/Adam + parameter all-gather by the two
         kernels of csrc/dp_optim.cu over NVLink peer memory; "nccl" = one NCCL all-reduce of the flat bucket, then the full
         Adam on every rank; "auto" = peer when the node's symmetric memory can be set up (all ranks agree), else nccl."""
@@ -192,6 +193,9 @@ class TrainStep:
         self.decoder.materialize_loss = False
         if hasattr(self.decoder, "direct_param_grads"):
             self.decoder.direct_param_grads = True         # parameter gradients of the LSTM land in the flat bucket directly
+            if hasattr(self.decoder, "defer_weight_grads") and defer_weight_grads and not overlap_all_reduce:
+                # the upper layers' weight-gradient GEMMs run on the SMs the lower layer's recurrence leaves idle (lstm.py)
+                self.decoder.defer_weight_grads = True
         self.last = {}
         # device-resident step counter = Philox offset of the reparameterisation noise: a captured CUDA graph then
         # draws fresh eps on every replay
@@ -241,6 +245,8 @@ class TrainStep:
         loss, kld, rec = self.losses(feats, rel)
         self._early_done = False
         loss.backward()
+        from . import lstm as _lstm
+        _lstm.flush_deferred()                                  # normally empty: the lowest LSTM layer's backward ran what was queued
         lossf = loss.detach().float().reshape(1)
         a = self.arena
         if self.dp_peer:
