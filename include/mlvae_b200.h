@@ -291,6 +291,7 @@ typedef struct mlvae_dp_adam_args {
 size_t mlvae_dp_sync_bytes(void);
 int mlvae_dp_adam_step(const mlvae_dp_adam_args *args, void *stream);
 int mlvae_dp_read_state(const void *d_sync, float out[5], void *stream);
+int mlvae_dp_set_adam_step(void *d_sync, float step, void *stream);   /* checkpoint resume: same value on every rank */
 int mlvae_dp_debug_max_ctas(int n);          /* tests: cap both grids so that several ranks simulated on ONE device stay co-resident */
 
 /* ------------------------------------------------------------------------- *

@@ -90,6 +90,7 @@ SIGNATURES = {
     "mlvae_dp_sync_bytes": (_sz, []),
     "mlvae_dp_adam_step": (_i, [C.POINTER(DpAdamArgs), _vp]),
     "mlvae_dp_read_state": (_i, [_vp, C.POINTER(C.c_float * 5), _vp]),
+    "mlvae_dp_set_adam_step": (_i, [_vp, C.c_float, _vp]),
     "mlvae_dp_debug_max_ctas": (_i, [_i]),
     "mlvae_adam_clip_step": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, C.c_float, C.c_double, C.c_double, C.c_double, C.c_double, C.c_float, _vp, _vp, _vp]),
     "mlvae_lstm_pack_weights": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp]),

@@ -310,4 +310,12 @@ int mlvae_dp_read_state(const void *d_sync, float out[5], void *stream) {
     return MLVAE_OK;
 }
 
+// Restore the Adam step count of a sync block (checkpoint resume); every rank sets the same value before the next step.
+int mlvae_dp_set_adam_step(void *d_sync, float step, void *stream) {
+    MLVAE_REQUIRE(d_sync && step >= 0.f, MLVAE_ERR_INVALID_ARG, "dp_set_adam_step: bad arguments");
+    MLVAE_CHECK_CUDA(cudaMemcpyAsync((char *)d_sync + offsetof(DpSync, step), &step, sizeof(float), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    MLVAE_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return MLVAE_OK;
+}
+
 }  // extern "C"

@@ -229,6 +229,38 @@ class TrainStep:
         self._early_done = True
         return None
 
+    # -- optimiser state (the reference registers the optimiser with its Checkpointer: models/md_model.py:50-52) ---------------
+    def optimizer_state_dict(self) -> dict:
+        """{'step', 'exp_avg', 'exp_avg_sq'} over the flat arena.  In the peer-memory data-parallel mode every rank updates (and so
+        holds) only its shard of the two moment buffers: the shards are gathered here, so EVERY rank must call this (collective)."""
+        a = self.arena
+        m, v = a.exp_avg.clone(), a.exp_avg_sq.clone()
+        if self.dp_peer:
+            import torch.distributed as dist
+            W, n = self.world_size, a.flat.numel()
+            per = -(-(n // 4) // W) * 4
+            for buf in (m, v):
+                pad = torch.zeros(per * W, dtype=buf.dtype, device=buf.device)
+                r = a.peer.rank
+                lo, hi = min(n, r * per), min(n, (r + 1) * per)
+                mine = torch.zeros(per, dtype=buf.dtype, device=buf.device)
+                mine[:hi - lo] = buf[lo:hi]
+                dist.all_gather_into_tensor(pad, mine)
+                buf.copy_(pad[:n])
+            step = a.peer.read_state()["step"]
+        else:
+            step = int(self.adam_state[0].item())
+        return {"step": step, "exp_avg": m, "exp_avg_sq": v}
+
+    def load_optimizer_state_dict(self, sd: dict):
+        a = self.arena
+        a.exp_avg.copy_(sd["exp_avg"].to(a.exp_avg.device))
+        a.exp_avg_sq.copy_(sd["exp_avg_sq"].to(a.exp_avg_sq.device))
+        if self.dp_peer:
+            L.check(L.lib().mlvae_dp_set_adam_step(L.ptr(a.peer.sync), float(sd["step"]), L.stream_ptr()), "mlvae_dp_set_adam_step", kernels=0)
+        else:
+            self.adam_state[0] = float(sd["step"])
+
     # -- forward pieces -------------------------------------------------------------------
     def features(self, wav, wav_lens):
         feats, rel = self.fbank(wav, wav_lens, truncate=True, out_dtype=torch.float32)

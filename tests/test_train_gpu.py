@@ -181,3 +181,42 @@ def test_train_step_cuda_graph_replays_are_training_steps(cuda):
     assert int(graphed.step_counter) == int(eager.step_counter)
     assert np.allclose(seq_e, seq_g, rtol=2e-2), (seq_e, seq_g)
     assert len(set(seq_g)) == len(seq_g)                                   # not a frozen replay
+
+
+def test_train_step_resume_from_checkpoint_state(cuda):
+    """Modules + normaliser + optimiser state + step counter restored into a fresh TrainStep: the next steps are bit-identical
+    to the uninterrupted run (models/md_model.py:50-52: the reference registers the optimiser with its Checkpointer)."""
+    from ml_vae_b200.features import Fbank
+    from ml_vae_b200.modules import Decoder, VanillaVAE
+    from ml_vae_b200.normalizer import InputNormalization
+    from ml_vae_b200.train_step import TrainStep
+
+    def make(seed):
+        torch.manual_seed(seed)
+        enc = VanillaVAE([80, 64, 64], 64).to(cuda)
+        dec = Decoder(64, 64, 2, 0.15, [128, 64, 64, 80]).to(cuda)
+        return TrainStep(Fbank(deltas=False, hop_length=10, n_mels=80), InputNormalization().to(cuda), enc, dec,
+                         {"kld_weight": 0.001, "batch_size": 8}, compute_dtype=torch.bfloat16, seed=5)
+
+    g = torch.Generator().manual_seed(3)
+    batches = [(0.1 * torch.randn(8, 8000, generator=g)).to(cuda) for _ in range(3)]
+    lens = torch.full((8,), 8000, dtype=torch.int32, device=cuda)
+    a = make(1)
+    for i in range(4):
+        a.step(batches[i % 3], lens)
+    ckpt = {"enc": {k: v.clone() for k, v in a.encoder.state_dict().items()}, "dec": {k: v.clone() for k, v in a.decoder.state_dict().items()},
+            "norm": {k: (v.clone() if torch.is_tensor(v) else v) for k, v in a.normalizer.state_dict().items()},
+            "opt": a.optimizer_state_dict(), "counter": a.step_counter.clone(), "calls": (a.encoder.calls, getattr(a.decoder, "dropout_calls", 0))}
+    assert ckpt["opt"]["step"] == 4
+    ref = [float(a.step(batches[i % 3], lens)) for i in range(4, 7)]
+    b = make(99)                                                           # different initial weights: everything must come from the checkpoint
+    b.encoder.load_state_dict(ckpt["enc"]); b.decoder.load_state_dict(ckpt["dec"]); b.normalizer.load_state_dict(ckpt["norm"])
+    b.arena.refresh_bf16()
+    b.load_optimizer_state_dict(ckpt["opt"])
+    b.step_counter.copy_(ckpt["counter"])
+    b.encoder.calls = ckpt["calls"][0]
+    if hasattr(b.decoder, "dropout_calls"):
+        b.decoder.dropout_calls = ckpt["calls"][1]
+    got = [float(b.step(batches[i % 3], lens)) for i in range(4, 7)]
+    assert got == ref, (got, ref)
+    assert torch.equal(a.arena.flat, b.arena.flat)
