@@ -104,6 +104,13 @@ int mlvae_reparam_kl_fwd(const void *d_mu, const void *d_logvar, const void *d_e
                          void *d_z, void *d_kl_elem, float *d_kl_out, void *d_scratch,
                          void *stream);
 
+/* Same with mu / logvar rows ld_in elements apart (0 = L): the two halves of ONE stacked (B,T,2L) projection output
+ * (modules/vanilla_vae.py:23-24 computed as one GEMM against [W_mu; W_logvar]) are read in place, d_logvar = d_mu + L. */
+int mlvae_reparam_kl_fwd_strided(const void *d_mu, const void *d_logvar, int64_t ld_in, const void *d_eps,
+                                 uint64_t seed, uint64_t offset, const uint64_t *d_offset_add, const float *d_lens,
+                                 int B, int T, int L, int dtype,
+                                 void *d_z, void *d_kl_elem, float *d_kl_out, void *d_scratch, void *stream);
+
 /*   g_elem   = d_grad_kl_elem (may be NULL) + d_grad_kl_mean[0] * mask / (count*L) (may be NULL)
  *   grad_mu     = grad_z + g_elem * mu
  *   grad_logvar = grad_z * 0.5*exp(0.5*logvar)*eps + g_elem * 0.5*(exp(logvar) - 1)
@@ -113,6 +120,13 @@ int mlvae_reparam_kl_bwd(const void *d_mu, const void *d_logvar, const void *d_e
                          const void *d_grad_kl_elem, const float *d_grad_kl_mean,
                          const float *d_lens, int B, int T, int L, int dtype,
                          void *d_grad_mu, void *d_grad_logvar, void *stream);
+/* Strided form: inputs as in mlvae_reparam_kl_fwd_strided, gradient rows ld_out elements apart (0 = L): both gradients land
+ * in one stacked (B,T,2L) buffer that feeds the projection's backward GEMMs without a concatenation pass. */
+int mlvae_reparam_kl_bwd_strided(const void *d_mu, const void *d_logvar, int64_t ld_in, const void *d_eps,
+                                 uint64_t seed, uint64_t offset, const uint64_t *d_offset_add,
+                                 const void *d_grad_z, const void *d_grad_kl_elem, const float *d_grad_kl_mean,
+                                 const float *d_lens, int B, int T, int L, int dtype,
+                                 void *d_grad_mu, void *d_grad_logvar, int64_t ld_out, void *stream);
 
 /* ------------------------------------------------------------------------- *
  * Fused reconstruction loss (+ length-masked mean).

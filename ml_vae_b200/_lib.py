@@ -62,6 +62,8 @@ SIGNATURES = {
     "mlvae_philox_normal_ex": (_i, [_u64, _u64, _i64, _vp, _i, _i, _vp]),
     "mlvae_reparam_kl_fwd": (_i, [_vp, _vp, _vp, _u64, _u64, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "mlvae_reparam_kl_bwd": (_i, [_vp, _vp, _vp, _u64, _u64, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "mlvae_reparam_kl_fwd_strided": (_i, [_vp, _vp, _i64, _vp, _u64, _u64, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "mlvae_reparam_kl_bwd_strided": (_i, [_vp, _vp, _i64, _vp, _u64, _u64, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _i64, _vp]),
     "mlvae_gmm_reparam_kl_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _u64, _u64, _vp, _i64, _i, _vp, _vp, _vp]),
     "mlvae_gmm_reparam_kl_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _u64, _u64, _vp, _vp, _vp, _i64, _i, _vp, _vp, _vp, _vp, _vp]),
     "mlvae_apply_weight_fwd": (_i, [_vp, _vp, _i64, _i, _i, _i, _vp, _vp]),

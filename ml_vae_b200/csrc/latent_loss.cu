@@ -221,14 +221,15 @@ template <typename T, int VEC>
 __global__ void __launch_bounds__(kThreads)
 reparam_kl_fwd_kernel(const T *__restrict__ mu, const T *__restrict__ logvar, const T *__restrict__ eps,
                       const PhiloxKey key, uint64_t offset, const uint64_t *__restrict__ offset_add, const float *__restrict__ lens, int B, int Tn, int L,
-                      T *__restrict__ z, T *__restrict__ kl_elem, float *__restrict__ kl_out, ReduceScratch *scratch) {
+                      int64_t ld_in, T *__restrict__ z, T *__restrict__ kl_elem, float *__restrict__ kl_out, ReduceScratch *scratch) {
     if (offset_add) offset += __ldg(offset_add);      // device-resident step counter (CUDA-graph friendly)
     float acc = 0.f;
     for (RowWalker w((int64_t)B * Tn, L / VEC, Tn); w.valid(); w.next()) {
         const int64_t e0 = w.vec * VEC;
+        const int64_t ei = ((int64_t)w.b * Tn + w.t) * ld_in + (int64_t)w.cv * VEC;      // mu / logvar rows are ld_in elements apart
         Chunk<T, VEC> m, lv, ep, zz, kk;
-        m.load(mu + e0);
-        lv.load(logvar + e0);
+        m.load(mu + ei);
+        lv.load(logvar + ei);
         if (eps) ep.load(eps + e0);
         else stream_eps<T, VEC>(e0, offset, key, ep.v);
         float maskf = 1.f;
@@ -256,15 +257,17 @@ __global__ void __launch_bounds__(kThreads)
 reparam_kl_bwd_kernel(const T *__restrict__ mu, const T *__restrict__ logvar, const T *__restrict__ eps,
                       const PhiloxKey key, uint64_t offset, const uint64_t *__restrict__ offset_add, const T *__restrict__ grad_z,
                       const T *__restrict__ grad_kl_elem, const float *__restrict__ grad_kl_mean,
-                      const float *__restrict__ lens, int B, int Tn, int L,
+                      const float *__restrict__ lens, int B, int Tn, int L, int64_t ld_in, int64_t ld_out,
                       T *__restrict__ grad_mu, T *__restrict__ grad_logvar) {
     if (offset_add) offset += __ldg(offset_add);
     const float gscale = mean_grad_scale(grad_kl_mean, lens, B, Tn, L);
     for (RowWalker w((int64_t)B * Tn, L / VEC, Tn); w.valid(); w.next()) {
         const int64_t e0 = w.vec * VEC;
+        const int64_t row = (int64_t)w.b * Tn + w.t;
+        const int64_t ei = row * ld_in + (int64_t)w.cv * VEC, eo = row * ld_out + (int64_t)w.cv * VEC;
         Chunk<T, VEC> m, lv, ep, gz, ge, gm, gl;
-        m.load(mu + e0);
-        lv.load(logvar + e0);
+        m.load(mu + ei);
+        lv.load(logvar + ei);
         if (grad_z) gz.load(grad_z + e0); else gz.zero();
         if (grad_kl_elem) ge.load(grad_kl_elem + e0); else ge.zero();
         if (eps) ep.load(eps + e0);
@@ -278,8 +281,8 @@ reparam_kl_bwd_kernel(const T *__restrict__ mu, const T *__restrict__ logvar, co
             gm.v[i] = fmaf(g, m.v[i], gz.v[i]);
             gl.v[i] = fmaf(gz.v[i] * 0.5f * sd, ep.v[i], g * 0.5f * (sd * sd - 1.f));
         }
-        gm.store(grad_mu + e0);
-        gl.store(grad_logvar + e0);
+        gm.store(grad_mu + eo);
+        gl.store(grad_logvar + eo);
     }
 }
 
@@ -671,18 +674,51 @@ int mlvae_philox_normal(uint64_t seed, uint64_t offset, int64_t n, void *d_out, 
     return mlvae_philox_normal_ex(seed, offset, n, d_out, dtype, dtype, stream);      // the stream the kernels of that dtype draw
 }
 
-int mlvae_reparam_kl_fwd(const void *d_mu, const void *d_logvar, const void *d_eps, uint64_t seed, uint64_t offset,
-                         const uint64_t *d_offset_add, const float *d_lens, int B, int T_, int L, int dtype, void *d_z, void *d_kl_elem,
-                         float *d_kl_out, void *d_scratch, void *stream) {
+int mlvae_reparam_kl_fwd_strided(const void *d_mu, const void *d_logvar, int64_t ld_in, const void *d_eps, uint64_t seed, uint64_t offset,
+                                 const uint64_t *d_offset_add, const float *d_lens, int B, int T_, int L, int dtype, void *d_z, void *d_kl_elem,
+                                 float *d_kl_out, void *d_scratch, void *stream) {
     if (int rc = check_btc(B, T_, L)) return rc;
     MLVAE_REQUIRE(d_mu && d_logvar && d_z, MLVAE_ERR_INVALID_ARG, "reparam_kl_fwd: mu, logvar and z are required");
     MLVAE_REQUIRE(!d_kl_out || (d_lens && d_scratch), MLVAE_ERR_INVALID_ARG, "reparam_kl_fwd: reduced KL needs lens and scratch");
-    const bool al = aligned16(d_mu) && aligned16(d_logvar) && aligned16(d_z) && aligned16(d_eps) && aligned16(d_kl_elem);
+    if (ld_in == 0) ld_in = L;
+    MLVAE_REQUIRE(ld_in >= L, MLVAE_ERR_INVALID_ARG, "reparam_kl_fwd: row stride %lld < L = %d", (long long)ld_in, L);
+    const int esz = dtype == MLVAE_F32 ? 4 : 2;
+    const bool al = aligned16(d_mu) && aligned16(d_logvar) && aligned16(d_z) && aligned16(d_eps) && aligned16(d_kl_elem) && (ld_in * esz) % 16 == 0;
     MLVAE_DISPATCH(dtype, L, al, {
         const int64_t nvec = (int64_t)B * T_ * (L / VEC);
         reparam_kl_fwd_kernel<T, VEC><<<grid_for(nvec), kThreads, 0, (cudaStream_t)stream>>>(
-            (const T *)d_mu, (const T *)d_logvar, (const T *)d_eps, PhiloxKey(seed), offset, d_offset_add, d_lens, B, T_, L, (T *)d_z,
+            (const T *)d_mu, (const T *)d_logvar, (const T *)d_eps, PhiloxKey(seed), offset, d_offset_add, d_lens, B, T_, L, ld_in, (T *)d_z,
             (T *)d_kl_elem, d_kl_out, (ReduceScratch *)d_scratch);
+    });
+    MLVAE_CHECK_CUDA(cudaGetLastError());
+    return MLVAE_OK;
+}
+
+int mlvae_reparam_kl_fwd(const void *d_mu, const void *d_logvar, const void *d_eps, uint64_t seed, uint64_t offset,
+                         const uint64_t *d_offset_add, const float *d_lens, int B, int T_, int L, int dtype, void *d_z, void *d_kl_elem,
+                         float *d_kl_out, void *d_scratch, void *stream) {
+    return mlvae_reparam_kl_fwd_strided(d_mu, d_logvar, 0, d_eps, seed, offset, d_offset_add, d_lens, B, T_, L, dtype, d_z, d_kl_elem, d_kl_out,
+                                        d_scratch, stream);
+}
+
+int mlvae_reparam_kl_bwd_strided(const void *d_mu, const void *d_logvar, int64_t ld_in, const void *d_eps, uint64_t seed, uint64_t offset,
+                                 const uint64_t *d_offset_add, const void *d_grad_z, const void *d_grad_kl_elem, const float *d_grad_kl_mean,
+                                 const float *d_lens, int B, int T_, int L, int dtype, void *d_grad_mu, void *d_grad_logvar, int64_t ld_out,
+                                 void *stream) {
+    if (int rc = check_btc(B, T_, L)) return rc;
+    MLVAE_REQUIRE(d_mu && d_logvar && d_grad_mu && d_grad_logvar, MLVAE_ERR_INVALID_ARG, "reparam_kl_bwd: missing buffers");
+    MLVAE_REQUIRE(!d_grad_kl_mean || d_lens, MLVAE_ERR_INVALID_ARG, "reparam_kl_bwd: reduced-KL gradient needs lens");
+    if (ld_in == 0) ld_in = L;
+    if (ld_out == 0) ld_out = L;
+    MLVAE_REQUIRE(ld_in >= L && ld_out >= L, MLVAE_ERR_INVALID_ARG, "reparam_kl_bwd: row strides must be >= L = %d", L);
+    const int esz = dtype == MLVAE_F32 ? 4 : 2;
+    const bool al = aligned16(d_mu) && aligned16(d_logvar) && aligned16(d_eps) && aligned16(d_grad_z) &&
+                    aligned16(d_grad_kl_elem) && aligned16(d_grad_mu) && aligned16(d_grad_logvar) && (ld_in * esz) % 16 == 0 && (ld_out * esz) % 16 == 0;
+    MLVAE_DISPATCH(dtype, L, al, {
+        const int64_t nvec = (int64_t)B * T_ * (L / VEC);
+        reparam_kl_bwd_kernel<T, VEC><<<grid_for(nvec), kThreads, 0, (cudaStream_t)stream>>>(
+            (const T *)d_mu, (const T *)d_logvar, (const T *)d_eps, PhiloxKey(seed), offset, d_offset_add, (const T *)d_grad_z,
+            (const T *)d_grad_kl_elem, d_grad_kl_mean, d_lens, B, T_, L, ld_in, ld_out, (T *)d_grad_mu, (T *)d_grad_logvar);
     });
     MLVAE_CHECK_CUDA(cudaGetLastError());
     return MLVAE_OK;
@@ -692,19 +728,8 @@ int mlvae_reparam_kl_bwd(const void *d_mu, const void *d_logvar, const void *d_e
                          const uint64_t *d_offset_add, const void *d_grad_z, const void *d_grad_kl_elem, const float *d_grad_kl_mean,
                          const float *d_lens, int B, int T_, int L, int dtype, void *d_grad_mu, void *d_grad_logvar,
                          void *stream) {
-    if (int rc = check_btc(B, T_, L)) return rc;
-    MLVAE_REQUIRE(d_mu && d_logvar && d_grad_mu && d_grad_logvar, MLVAE_ERR_INVALID_ARG, "reparam_kl_bwd: missing buffers");
-    MLVAE_REQUIRE(!d_grad_kl_mean || d_lens, MLVAE_ERR_INVALID_ARG, "reparam_kl_bwd: reduced-KL gradient needs lens");
-    const bool al = aligned16(d_mu) && aligned16(d_logvar) && aligned16(d_eps) && aligned16(d_grad_z) &&
-                    aligned16(d_grad_kl_elem) && aligned16(d_grad_mu) && aligned16(d_grad_logvar);
-    MLVAE_DISPATCH(dtype, L, al, {
-        const int64_t nvec = (int64_t)B * T_ * (L / VEC);
-        reparam_kl_bwd_kernel<T, VEC><<<grid_for(nvec), kThreads, 0, (cudaStream_t)stream>>>(
-            (const T *)d_mu, (const T *)d_logvar, (const T *)d_eps, PhiloxKey(seed), offset, d_offset_add, (const T *)d_grad_z,
-            (const T *)d_grad_kl_elem, d_grad_kl_mean, d_lens, B, T_, L, (T *)d_grad_mu, (T *)d_grad_logvar);
-    });
-    MLVAE_CHECK_CUDA(cudaGetLastError());
-    return MLVAE_OK;
+    return mlvae_reparam_kl_bwd_strided(d_mu, d_logvar, 0, d_eps, seed, offset, d_offset_add, d_grad_z, d_grad_kl_elem, d_grad_kl_mean, d_lens, B, T_, L,
+                                        dtype, d_grad_mu, d_grad_logvar, 0, stream);
 }
 
 int mlvae_recon_fwd(const void *d_mean, const void *d_logvar, const void *d_target, const float *d_lens, int B, int T_,

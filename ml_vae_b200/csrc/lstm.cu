@@ -32,9 +32,9 @@
 // successive uses of a slot and differs from the zeroed initial state.  Every element is validated on its own,
 // so the protocol does not depend on store atomicity.  A NaN h (the only value with bit 14 set) travels as 0; the
 // output Y keeps the NaN, so the loss is non-finite exactly when the reference's is.  The backward pass ships its
-// partial dh sums the same way: scaled by 2^-64 and saturated below 2 so that bit 14 is free as well (the sums
-// are rescaled by 2^64 on arrival; gradients below 2^-62 flush to zero), 8 rows of two (producer, unit) pairs per
-// 32-byte sector.  Deterministic: fixed summation orders, no data atomics.
+// partial dh sums the same way: scaled by 2^-64 (folded into the resident transposed weights, an exact power-of-two
+// scaling) so that bit 14 is free as well (the sums are rescaled by 2^64 on arrival; gradients below 2^-62 flush to
+// zero), 8 rows of two (producer, unit) pairs per 32-byte sector.  Deterministic: fixed summation orders, no data atomics.
 // All CTAs wait on each other, so the launch is cooperative (co-residency guaranteed or refused).
 #include <cooperative_groups.h>
 
@@ -378,9 +378,10 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_fwd_kernel(LstmFwdParams
 // ======================================================================================
 // Backward recurrence.  Same CTAs / chains / ownership as the forward pass.  Per step (reverse order), per chain:
 //   consume  every thread pulls ONE sector: the 8 rows' partial dh sums one producer computed for two of this CTA's
-//            units; a shared-memory exchange + one named barrier inside the chain, then thread (row j = warp, unit)
-//            adds the G partials in fixed producer order
-//   phase A  thread = (batch row j, unit): dh = dY + dh_rec; gate gradients -> pre-activation gradients
+//            units.  The 16 producers of a unit pair sit in the 16 lanes of a half warp: a reduce-scatter butterfly
+//            (4 rounds, 11 SHFL, fixed tree = deterministic) leaves every lane the sum of ONE (unit, batch row) -- no
+//            shared-memory round trip, no barrier across the chain's warps
+//   phase A  thread = (unit 4 gw + lane / 8, batch row lane % 8): dh = dY + dh_rec; gate gradients -> pre-activation gradients
 //            da_{i,f,g,o}; written (bf16) over the saved gates in G (input of the weight / input GEMMs that follow)
 //            and into the chain's K-major B-operand tile (16 x 128 gate rows, rows 8..15 zero); mbarrier hand-off
 //   phase B  partial[jh, j] = sum_{r in my 128 gate rows} W_hh[r, jh] * da[j, r]   tcgen05.mma with the TRANSPOSED
@@ -394,19 +395,23 @@ struct LstmBwdParams {
     const float *C;          // (B, T, 2H) cell states from the forward pass
     const bf16 *dY;          // (B, T, 2H) gradient of the layer output
     const bf16 *Whh;         // (2, 4H, H)
-    uint4 *ll;               // [2 parity][groups][G owners][G producers][32 units] zeroed 16-byte words = 8 rows of tagged bf16
+    uint4 *ll;               // [2 parity][groups][G owners][8 unit quads][G producers][4 units] zeroed 16-byte words = 8 rows of tagged bf16
     float *db_part;          // (slices, 2, 4H) per-16-row-slice sums over (rows, t) of dA, torch gate order; or nullptr
     int B, T, H;
     int poll_delay;
 };
 
-constexpr float kWireScale = 5.421010862427522e-20f;      // 2^-64: partial dh sums travel below 2.0 (bit 14 of the bf16 free)
 constexpr float kWireUnscale = 18446744073709551616.f;    // 2^64
+// The partial dh sums travel as bf16 scaled by 2^-64 so that they stay below 2.0 (bit 14 of the bf16 free for the tag).  The scale
+// is folded into the resident weights (exact: a power of two), so the accumulators come out of TMEM already scaled and packing a
+// pair is one convert + one logic op on the critical path.  Weights below 2^-62 flush to zero.
+__device__ __forceinline__ uint32_t bf16_scale_down64(uint32_t x) {      // bf16 bit pattern * 2^-64
+    return ((x >> 7) & 0xffu) > 64u ? x - (64u << 7) : (x & 0x8000u);
+}
 __device__ __forceinline__ uint32_t wire_pack(float x0, float x1, uint32_t tag) {
-    // scale, saturate below 2 (bf16 0x3FFF = 1.9921875; also maps NaN to a finite value: the NaN is already recorded in
-    // dA of this row / step, which is what makes the weight gradients non-finite), round to bf16, tag
-    x0 = fminf(fmaxf(x0 * kWireScale, -1.9921875f), 1.9921875f);
-    x1 = fminf(fmaxf(x1 * kWireScale, -1.9921875f), 1.9921875f);
+    // round to bf16, force the tag bit.  A non-finite sum (exponent MSB set) becomes a huge finite value on arrival; the NaN / Inf is
+    // already recorded in dA of this row / step, which is what makes the weight gradients non-finite.  Finite sums of 2^65 and
+    // more (no training run survives those) are not representable on the wire.
     const __nv_bfloat162 pk = __floats2bfloat162_rn(x0, x1);
     return (*reinterpret_cast<const uint32_t *>(&pk) & ~kTagBits) | tag;
 }
@@ -414,7 +419,7 @@ __device__ __forceinline__ uint32_t wire_pack(float x0, float x1, uint32_t tag) 
 template <bool kProf>
 __global__ void __launch_bounds__(kLstmThreads, 1) lstm_bwd_kernel(LstmBwdParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ uint64_t s_da[kChains], s_mma[kChains], s_free[kChains];
+    __shared__ uint64_t s_da[kChains][2], s_mma[kChains], s_free[kChains];
     __shared__ uint32_t s_tmem;
     const int H = p.H, T = p.T, B = p.B;
     const int G = H / kUnits;
@@ -431,9 +436,7 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_bwd_kernel(LstmBwdParams
     const int tiles = (H + 127) / 128;
 
     constexpr int kDaBytes = kMmaN * 128 * 2;                                        // 4 KB per chain
-    constexpr int kPartFloats = 16 * kChainRows * 32;                                // [16 producers][8 rows][32 units] per chain
     unsigned char *sDA = smem + chain * kDaBytes;                                    // 16 x 128 bf16, K-major
-    float *s_part = reinterpret_cast<float *>(smem + kChains * kDaBytes) + chain * kPartFloats;
 
     const uint32_t dcol = (uint32_t)((tiles * 64 + 31) & ~31);
     uint32_t tmem_cols = 32;
@@ -441,7 +444,8 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_bwd_kernel(LstmBwdParams
     if (warp == 0) tc::tmem_alloc(&s_tmem, tmem_cols);
     if (tid == 0) {
         for (int c = 0; c < kChains; ++c) {
-            tc::mbar_init(&s_da[c], kGateWarps);
+            tc::mbar_init(&s_da[c][0], kGateWarps / 2);      // wave 0: gate warps 0..3 = units 0..15 = the even K-steps
+            tc::mbar_init(&s_da[c][1], kGateWarps / 2);      // wave 1: gate warps 4..7 = units 16..31 = the odd K-steps
             tc::mbar_init(&s_mma[c], tiles < kIssuers ? tiles : kIssuers);       // one commit per issuer warp that owns M-tiles
             tc::mbar_init(&s_free[c], kGateWarps);
         }
@@ -467,8 +471,8 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_bwd_kernel(LstmBwdParams
                     uint32_t lo = 0, hi = 0;
                     if (jh < H) {
                         const int r0 = k16 * 16 + 2 * e, r1 = r0 + 1;
-                        lo = W16[((size_t)(r0 >> 5) * H + u * kUnits + (r0 & 31)) * H + jh];
-                        hi = W16[((size_t)(r1 >> 5) * H + u * kUnits + (r1 & 31)) * H + jh];
+                        lo = bf16_scale_down64(W16[((size_t)(r0 >> 5) * H + u * kUnits + (r0 & 31)) * H + jh]);
+                        hi = bf16_scale_down64(W16[((size_t)(r1 >> 5) * H + u * kUnits + (r1 & 31)) * H + jh]);
                     }
                     v[e] = lo | (hi << 16);
                 }
@@ -498,14 +502,25 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_bwd_kernel(LstmBwdParams
             long long tprev = clock64(), pacc[4] = {0, 0, 0, 0};
             for (int step = 0; step + 1 < T; ++step) {                               // the last step ships no partials
                 if (step > 0) tc::mbar_wait(&s_free[chain], (step - 1) & 1);         // previous partials have left TMEM
-                tc::mbar_wait(&s_da[chain], step & 1);                               // all 8 warps wrote their dA rows
+                // K index = gate * 32 + unit: the even K-steps hold units 0..15 (gate warps 0..3), the odd ones units 16..31
+                tc::mbar_wait(&s_da[chain][0], step & 1);
                 tc::fence_after_sync();
                 PROF_MARK(0);                                                        // issuer: wait for dA
                 if (tc::elect_one()) {
                     for (int m = iw; m < tiles; m += kIssuers) {
 #pragma unroll
-                        for (int k16 = 0; k16 < 8; ++k16)
+                        for (int k16 = 0; k16 < 8; k16 += 2)
                             tc::mma_bf16_ts(d_tile0 + m * kMmaN, tmem + m * 64 + k16 * 8, b_desc0 + (uint64_t)(k16 * 16), idesc, k16 > 0);
+                    }
+                }
+                __syncwarp();
+                tc::mbar_wait(&s_da[chain][1], step & 1);
+                tc::fence_after_sync();
+                if (tc::elect_one()) {
+                    for (int m = iw; m < tiles; m += kIssuers) {
+#pragma unroll
+                        for (int k16 = 1; k16 < 8; k16 += 2)
+                            tc::mma_bf16_ts(d_tile0 + m * kMmaN, tmem + m * 64 + k16 * 8, b_desc0 + (uint64_t)(k16 * 16), idesc, 1);
                     }
                     tc::mma_commit(&s_mma[chain]);
                 }
@@ -515,8 +530,8 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_bwd_kernel(LstmBwdParams
             if constexpr (kProf) { if (prof) { prof[0] += pacc[0]; prof[1] += pacc[1]; } }
         }
     } else if (active) {
-        // phase-A identity of this thread: batch row j = gw, unit = lane
-        const int j = gw, unit = lane;
+        // phase-A identity of this thread = where the reduce-scatter leaves its sum: unit 4 gw + lane / 8, batch row lane % 8
+        const int j = lane & 7, unit = 4 * gw + (lane >> 3);
         const int b = min(b0 + j, B - 1);                 // rows past B are clamped for loads, never stored
         const bool row_ok = (b0 + j) < B;
         uint2 *G2 = reinterpret_cast<uint2 *>(p.G);
@@ -526,14 +541,23 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_bwd_kernel(LstmBwdParams
         const ptrdiff_t y_step = (ptrdiff_t)(d ? 1 : -1) * 2 * H;
         size_t g_off = (((size_t)b * T + t_first) * 2 + d) * (size_t)H + u * kUnits + unit;        // 8-byte units: (B,T,2,H,4)
         size_t y_off = ((size_t)b * T + t_first) * (2 * H) + d * H + u * kUnits + unit;
-        // consumer identity: thread ci = gw*32 + lane pulls the sector of producer ci / 16, units 2*(ci % 16), 2*(ci % 16) + 1
-        const int ci = gw * 32 + lane;
-        const bool c_has = ci < G * 16;
-        const int c_pr = ci >> 4, c_u0 = 2 * (ci & 15);
+        // consumer identity: lane pulls the sector of producer lane % 16, units 4 gw + 2 (lane / 16), + 1: the 16 producers of a unit
+        // pair are the 16 lanes of a half warp
+        const int c_pr = lane & 15, c_u0 = 4 * gw + 2 * (lane >> 4);
+        const bool c_has = c_pr < G;
         // producer identity: the warps with part == 0 ship the M-tiles 0, 1 and those with part == 1 the tiles 2, 3, each thread ALL
         // eight rows of unit `lane` of owner 4m+q: one 16-byte word per thread, 512 contiguous bytes (16 whole sectors) per warp store
         uint4 *const base0 = p.ll + (size_t)group * ll_words, *const base1 = base0 + (size_t)groups * ll_words;
-        const size_t src_o = (size_t)u * G * 32 + 2 * (size_t)(c_has ? ci : 0), dst_o = (size_t)u * 32 + lane;
+#ifndef MLVAE_LSTM_BWD_LAYOUT_V1
+        // exchange layout per group and parity: word [owner][unit quad = unit / 4][producer][unit % 4]: the 32 sectors a consumer warp
+        // polls (unit quad gw, all producers) are ONE contiguous kilobyte = 8 whole 128-byte lines per poll instruction (with the
+        // producer-major layout [owner][producer][unit] they were 16 half lines, twice the L2 request count under the polling load);
+        // a producer warp store covers 8 x 64 contiguous bytes (whole sectors)
+        const size_t src_o = (((size_t)u * 8 + gw) * G + (c_has ? c_pr : 0)) * 4 + 2 * (lane >> 4);
+        const size_t dst_o = ((size_t)(lane >> 2) * G + u) * 4 + (lane & 3);       // + owner * G * 32
+#else
+        const size_t src_o = (size_t)u * G * 32 + (size_t)(c_has ? c_pr : 0) * 32 + c_u0, dst_o = (size_t)u * 32 + lane;
+#endif
         const uint4 *const src0 = base0 + src_o, *const src1 = base1 + src_o;
         uint4 *const dst0 = base0 + dst_o, *const dst1 = base1 + dst_o;       // + owner * G * 32
 
@@ -563,25 +587,39 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_bwd_kernel(LstmBwdParams
                 }
                 PROF_MARK(0);                               // exchange wait
                 {
-                    // lo = rows 0..7 of unit c_u0, hi = rows 0..7 of unit c_u0 + 1 (bf16 pairs): one float2 store per row
-                    const uint32_t l4[4] = {lo.x, lo.y, lo.z, lo.w}, h4[4] = {hi.x, hi.y, hi.z, hi.w};
-                    float2 *dstp = reinterpret_cast<float2 *>(s_part + ((c_has ? c_pr : 0) * kChainRows) * 32 + c_u0);
-                    if (c_has) {
+                    // lo = rows 0..7 of unit c_u0, hi = rows 0..7 of unit c_u0 + 1 (bf16 pairs) from producer lane % 16.
+                    // Reduce-scatter over the 16 producers: round 1 (xor 8) trades whole packed words and settles the unit,
+                    // rounds 2..4 (xor 4, 2, 1) halve the rows; both partners of a pair add the same two numbers.
+                    const bool k1 = lane & 8, k2 = lane & 4, k3 = lane & 2, k4 = lane & 1;
+                    const uint4 mine = k1 ? hi : lo, send = k1 ? lo : hi;
+                    uint4 got;
+                    got.x = __shfl_xor_sync(0xffffffffu, send.x, 8);
+                    got.y = __shfl_xor_sync(0xffffffffu, send.y, 8);
+                    got.z = __shfl_xor_sync(0xffffffffu, send.z, 8);
+                    got.w = __shfl_xor_sync(0xffffffffu, send.w, 8);
+                    const uint32_t a4[4] = {mine.x, mine.y, mine.z, mine.w}, b4[4] = {got.x, got.y, got.z, got.w};
+                    float f[8];
 #pragma unroll
-                        for (int r = 0; r < 4; ++r) {
-                            dstp[(2 * r) * 16] = make_float2(__uint_as_float(l4[r] << 16), __uint_as_float(h4[r] << 16));
-                            dstp[(2 * r + 1) * 16] = make_float2(__uint_as_float(l4[r] & 0xffff0000u), __uint_as_float(h4[r] & 0xffff0000u));
-                        }
+                    for (int r = 0; r < 4; ++r) {
+                        f[2 * r] = __uint_as_float(a4[r] << 16) + __uint_as_float(b4[r] << 16);
+                        f[2 * r + 1] = __uint_as_float(a4[r] & 0xffff0000u) + __uint_as_float(b4[r] & 0xffff0000u);
                     }
+                    float g4[4];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const float keep = k2 ? f[4 + r] : f[r], give = k2 ? f[r] : f[4 + r];
+                        g4[r] = keep + __shfl_xor_sync(0xffffffffu, give, 4);
+                    }
+                    float g2[2];
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        const float keep = k3 ? g4[2 + r] : g4[r], give = k3 ? g4[r] : g4[2 + r];
+                        g2[r] = keep + __shfl_xor_sync(0xffffffffu, give, 2);
+                    }
+                    const float keep = k4 ? g2[1] : g2[0], give = k4 ? g2[0] : g2[1];
+                    dh_rec = (keep + __shfl_xor_sync(0xffffffffu, give, 1)) * kWireUnscale;      // unit 4 gw + lane / 8, row lane % 8
                 }
-                named_bar_sync(1 + chain, kGateWarps * 32);
-                {
-                    const float *sp = s_part + j * 32 + unit;            // [producer][row j][unit], producer stride 256
-                    float acc = 0.f;
-                    for (int pr = 0; pr < G; ++pr) acc += sp[pr * (kChainRows * 32)];   // fixed producer order
-                    dh_rec = acc * kWireUnscale;
-                }
-                PROF_MARK(1);                               // reduction across the chain's warps
+                PROF_MARK(1);                               // reduce-scatter inside the warp
             }
             // ---- phase A: gate gradients ----
             const float gi = __uint_as_float(rg.x << 16), gf = __uint_as_float(rg.x & 0xffff0000u);
@@ -607,7 +645,7 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_bwd_kernel(LstmBwdParams
                 for (int g = 0; g < 4; ++g) *reinterpret_cast<bf16 *>(sDA + tc::kmajor_off(j, g * 32 + unit, 128)) = dab[g];
                 tc::fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) tc::mbar_arrive(&s_da[chain]);
+                if (lane == 0) tc::mbar_arrive(&s_da[chain][gw >> 2]);
             }
             // global side effects of phase A, after the hand-off to the issuer
             if (row_ok) {
@@ -660,8 +698,9 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_bwd_kernel(LstmBwdParams
         // bias gradient of this CTA's 128 gate rows over its 16-row slice: fixed-order sum over the 16 (chain, row) warps
         float *s_b = reinterpret_cast<float *>(smem);                    // [16 rows][4 gates][32 units], reuses the operand tiles
         if (!issuer) {
+            const int r = chain * kChainRows + (lane & 7), un = 4 * gw + (lane >> 3);      // this thread's (row of the slice, unit)
 #pragma unroll
-            for (int g = 0; g < 4; ++g) s_b[(warp * 4 + g) * 32 + lane] = active ? bsum[g] : 0.f;
+            for (int g = 0; g < 4; ++g) s_b[(r * 4 + g) * 32 + un] = active ? bsum[g] : 0.f;
         }
         __syncthreads();
         if (tid < 128) {
@@ -701,7 +740,7 @@ int lstm_plan(int B, int H, LstmPlan &pl) {
                   "lstm: batch %d x hidden %d needs %d co-resident CTAs (> %d SMs)", B, H, pl.G * pl.slices * 2, sms);
     const size_t groups = (size_t)2 * pl.slices * kChains;
     pl.smem_fwd = (size_t)kChains * kMmaN * H * 2;
-    pl.smem_bwd = (size_t)kChains * (kMmaN * 128 * 2 + 16 * kChainRows * 32 * sizeof(float));   // dA tiles + partial exchange (>= the bias reduction's 8 KB)
+    pl.smem_bwd = (size_t)kChains * kMmaN * 128 * 2;                                // dA tiles = 8 KB (also holds the bias reduction's 8 KB)
     pl.ll_fwd = 2 * groups * pl.G * 32 * sizeof(uint4);
     pl.ll_bwd = 2 * groups * (size_t)pl.G * pl.G * 32 * sizeof(uint4);
     return MLVAE_OK;

@@ -254,7 +254,9 @@ class _BiLSTMLayer(torch.autograd.Function):
             g_b = [torch.zeros(H4, dtype=torch.float32, device=dev) for _ in range(4)]
         # dW_ih[d] = dA[:, d]^T x: both operands MN-major; few output tiles for a narrow input -> split the B*T reduction
         # With ``defer_weight_grads`` (and gradients accumulated in place) the products are only queued: the backward of the layer
-        # below runs them beside its recurrence on the SMs that launch leaves idle (dW_hh always; dW_ih too when most SMs are idle).
+        # below runs them beside its recurrence on the SMs that launch leaves idle -- when there are enough of them: with 20 idle SMs
+        # (configs[1]) the GEMM's L2 traffic slows the latency-bound recurrence by 0.09 ms while hiding 0.13 ms, not worth the
+        # disturbed kernel; with 116 idle SMs (configs[3]) both products disappear under the recurrence (15.3 -> 14.9 ms per step).
         free = idle_sms(B, H, dev) if (ctx.defer_weight_grads and direct) else 0
 
         def dw_ih(max_ctas=0):
@@ -277,7 +279,7 @@ class _BiLSTMLayer(torch.autograd.Function):
         else:
             dw_ih()
         if T > 1:
-            if free >= 16:
+            if free >= 32:
                 _DEFERRED.append(dw_hh)
             else:
                 dw_hh()

@@ -71,18 +71,23 @@ class VanillaVAE(nn.Module):
         heads = arena.linear_views([self.mean_fc.weight, self.log_var_fc.weight], [self.mean_fc.bias, self.log_var_fc.bias])
         self._direct = (trunk, heads) if heads is not None and all(v is not None for v in trunk) else None
 
+    def _project_stacked(self, feats):
+        """Arena-bound bf16 path: [mean | log_var] as ONE (B, T, 2L) tensor (one GEMM against the adjacent head weights), or None."""
+        direct = getattr(self, "_direct", None)
+        if direct is None or feats.dtype != torch.bfloat16:
+            return None
+        trunk, heads = direct
+        if len(trunk) == 2 and mlp_chain.supported(trunk[0][0].shape[1], trunk[0][0].shape[0], trunk[1][0].shape[0]):
+            h, = mlp_chain.chain2(feats, [trunk[0]], [trunk[1]], act_b=True)      # fused trunk (csrc/mlp_chain.cu)
+        else:
+            h = direct_chain(feats, trunk, end_activation=True)
+        return linear_direct(h, heads)
+
     def project(self, feats):
         """feats (B, T, C) -> mean, log_var (B, T, L).  vanilla_vae.py:22-24."""
-        direct = getattr(self, "_direct", None)
-        if direct is not None and feats.dtype == torch.bfloat16:
-            trunk, heads = direct
-            if len(trunk) == 2 and mlp_chain.supported(trunk[0][0].shape[1], trunk[0][0].shape[0], trunk[1][0].shape[0]):
-                h, = mlp_chain.chain2(feats, [trunk[0]], [trunk[1]], act_b=True)      # fused trunk (csrc/mlp_chain.cu)
-            else:
-                h = direct_chain(feats, trunk, end_activation=True)
-            ml = linear_direct(h, heads)
-            mean, log_var = ml[..., : self.latent_size], ml[..., self.latent_size:]
-            return mean.contiguous(), log_var.contiguous()
+        ml = self._project_stacked(feats)
+        if ml is not None:
+            return ml[..., : self.latent_size].contiguous(), ml[..., self.latent_size:].contiguous()
         ws, bs = self._trunk()
         h = linear_chain(feats, ws, bs, end_activation=True)
         # both heads read h once: one GEMM against the stacked (2L, H) weight
@@ -93,14 +98,23 @@ class VanillaVAE(nn.Module):
         return mean.contiguous(), log_var.contiguous()
 
     def forward(self, feats, lens=None, eps=None):
-        mean, log_var = self.project(feats)
         # with a device step counter the kernel adds it to `offset`; the host call count moves to the high word so that
         # repeated forwards between two counter increments (eval batches, gradient accumulation) still get fresh eps
         offset = (self.calls << 32) if self.offset_dev is not None else self.calls
         self.calls += 1
-        z, kl_elem, kl_mean = ops.reparam_kl(mean, log_var, lens=lens, eps=eps, seed=self.seed, offset=offset,
-                                             want_elem=self.materialize_loss, want_mean=lens is not None,
-                                             offset_dev=self.offset_dev)
+        ml = self._project_stacked(feats)
+        if ml is not None:
+            # the kernel reads both halves of the stacked projection in place and its backward writes one stacked gradient:
+            # 'mean' / 'log_var' are views (no slice copies, no zero-fill + scatter + add of slice gradients in backward)
+            mean, log_var = ml[..., : self.latent_size], ml[..., self.latent_size:]
+            z, kl_elem, kl_mean = ops.reparam_kl_stacked(ml, lens=lens, eps=eps, seed=self.seed, offset=offset,
+                                                         want_elem=self.materialize_loss, want_mean=lens is not None,
+                                                         offset_dev=self.offset_dev)
+        else:
+            mean, log_var = self.project(feats)
+            z, kl_elem, kl_mean = ops.reparam_kl(mean, log_var, lens=lens, eps=eps, seed=self.seed, offset=offset,
+                                                 want_elem=self.materialize_loss, want_mean=lens is not None,
+                                                 offset_dev=self.offset_dev)
         out = {"mean": mean, "log_var": log_var, "sampled_h": z, "loss": kl_elem}
         if lens is not None:
             out["kld_loss"] = kl_mean

@@ -92,6 +92,67 @@ class _ReparamKL(torch.autograd.Function):
         return gmu, glv, None, None, None, None, None, None, None
 
 
+class _ReparamKLStacked(torch.autograd.Function):
+    """reparam + KL reading mean | log_var as the two halves of ONE (B, T, 2L) projection output (the stacked-head GEMM of
+    modules/vanilla_vae.py:23-24) in place, and writing both gradients into one (B, T, 2L) buffer that feeds that GEMM's
+    backward: no slice copies forward, no zero-fill / scatter / add of slice gradients backward."""
+
+    @staticmethod
+    def forward(ctx, ml, eps, lens, seed, offset, want_elem, want_mean, offset_dev=None):
+        L.require_cuda(ml, eps)
+        ml = _c(ml)
+        B, T, C2 = _btc(ml)
+        if C2 % 2:
+            raise ValueError("stacked mean | log_var needs an even channel count")
+        C = C2 // 2
+        shape = tuple(ml.shape[:-1]) + (C,)
+        if eps is not None:
+            eps = eps.to(ml.dtype).reshape(shape).contiguous()
+        z = torch.empty(shape, dtype=ml.dtype, device=ml.device)
+        kl_elem = torch.empty_like(z) if want_elem else None
+        kl_out = torch.empty(3, dtype=torch.float32, device=ml.device) if want_mean else None
+        lens_f = _lens(lens, ml) if lens is not None else None
+        if want_mean and lens_f is None:
+            raise ValueError("reduced KL needs lens")
+        half = C * ml.element_size()
+        L.check(L.lib().mlvae_reparam_kl_fwd_strided(
+            ml.data_ptr(), ml.data_ptr() + half, C2, L.ptr(eps), seed, offset, L.ptr(offset_dev), L.ptr(lens_f), B, T, C,
+            L.dtype_code(ml), L.ptr(z), L.ptr(kl_elem), L.ptr(kl_out), L.ptr(L.reduce_scratch(ml.device)) if want_mean else None,
+            L.stream_ptr()), "mlvae_reparam_kl_fwd_strided")
+        ctx.save_for_backward(ml, eps, lens_f)
+        ctx.seed, ctx.offset, ctx.offset_dev = seed, offset, offset_dev
+        ctx.set_materialize_grads(False)
+        empty = ml.new_empty(0)
+        return z, (kl_elem if want_elem else empty), (kl_out[0] if want_mean else empty.float())
+
+    @staticmethod
+    def backward(ctx, gz, gelem, gmean):
+        ml, eps, lens_f = ctx.saved_tensors
+        B, T, C2 = _btc(ml)
+        C = C2 // 2
+        gz = _c(gz)
+        gelem = _c(gelem) if gelem is not None and gelem.numel() else None
+        gmean = gmean.contiguous().float() if gmean is not None and gmean.numel() else None
+        if gz is not None and gz.dtype != ml.dtype:
+            gz = gz.to(ml.dtype)
+        if gelem is not None and gelem.dtype != ml.dtype:
+            gelem = gelem.to(ml.dtype)
+        gml = torch.empty_like(ml)
+        half = C * ml.element_size()
+        L.check(L.lib().mlvae_reparam_kl_bwd_strided(
+            ml.data_ptr(), ml.data_ptr() + half, C2, L.ptr(eps), ctx.seed, ctx.offset, L.ptr(ctx.offset_dev), L.ptr(gz), L.ptr(gelem),
+            L.ptr(gmean), L.ptr(lens_f), B, T, C, L.dtype_code(ml), gml.data_ptr(), gml.data_ptr() + half, C2, L.stream_ptr()),
+            "mlvae_reparam_kl_bwd_strided")
+        return gml, None, None, None, None, None, None, None
+
+
+def reparam_kl_stacked(ml, lens=None, eps=None, seed: int = 0, offset: int = 0,
+                       want_elem: bool = False, want_mean: bool = True, offset_dev=None):
+    """``reparam_kl`` on ml = [mean | log_var] (B, T, 2L), read in place -> (z, kl_elem | None, kl_mean | None)."""
+    z, e, m = _ReparamKLStacked.apply(ml, eps, lens, int(seed), int(offset), want_elem, want_mean, offset_dev)
+    return z, (e if want_elem else None), (m if want_mean else None)
+
+
 def reparam_kl(mu, logvar, lens=None, eps=None, seed: int = 0, offset: int = 0,
                want_elem: bool = False, want_mean: bool = True, offset_dev=None):
     """-> (z, kl_elem | None, kl_mean | None).  eps=None draws Philox(seed, offset [+ offset_dev[0], a device

@@ -57,8 +57,8 @@ def run(B, T, In, H, time_it=False):
         print("   bwd cycles/step:", dict(zip(["exchange wait", "reduce", "gate grads + hand-off", "mma completion + scatter", "issuer 0: wait dA", "issuer 0: issue + commit", "issuer 1: wait dA", "issuer 1: issue + commit"], [round(v / T) for v in prof.cpu().tolist()[:8]])))
         pc = prof.cpu().tolist()
         print("   per CTA of group 0 (gate warp 0, chain 0) [wait, reduce, gates, mma+scatter]:")
-        for x in range(H // 32):
-            print("     cta", x, [round(v / T) for v in pc[12 + 4 * x: 16 + 4 * x]])
+        for cta in range(H // 32):
+            print("     cta", cta, [round(v / T) for v in pc[12 + 4 * cta: 16 + 4 * cta]])
         print("   per gate warp of CTA 0 chain 0:")
         for w in range(1, 8):
             print("     warp", w, [round(v / T) for v in pc[76 + 4 * w: 80 + 4 * w]])

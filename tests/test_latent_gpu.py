@@ -54,6 +54,35 @@ def test_reparam_kl_fwd_bwd_vs_oracle(cuda, B, T, L, dtype):
     assert_close(lv_d.grad.float(), lv_r.grad, rtol, "grad_logvar")
 
 
+@pytest.mark.parametrize("B,T,L", [(4, 30, 64), (2, 7, 5), (3, 50, 256), (2, 9, 12)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("philox", [False, True])
+def test_reparam_kl_stacked_is_bit_identical_to_split(cuda, B, T, L, dtype, philox):
+    """mlvae_reparam_kl_{fwd,bwd}_strided on [mean | log_var] (B, T, 2L) read in place (vanilla_vae.py:23-24 as ONE stacked
+    projection) == the contiguous entry points on the two slices, bit for bit (same kernel, same arithmetic), incl. odd L
+    (scalar path) and the Philox stream."""
+    from ml_vae_b200 import ops
+    g = torch.Generator().manual_seed(7 * B + T + L)
+    ml = torch.randn(B, T, 2 * L, generator=g).clamp(-4, 3).to(dtype).to(cuda)
+    eps = None if philox else torch.randn(B, T, L, generator=g).to(dtype).to(cuda)
+    lens = _lens(B, T, 11).to(cuda)
+    gz = torch.randn(B, T, L, generator=g).to(dtype).to(cuda)
+    ge = torch.randn(B, T, L, generator=g).to(dtype).to(cuda)
+
+    a = ml.clone().requires_grad_(True)
+    z1, e1, m1 = ops.reparam_kl_stacked(a, lens=lens, eps=eps, seed=99, offset=3, want_elem=True, want_mean=True)
+    ((z1.float() * gz.float()).sum() + (e1.float() * ge.float()).sum() + 0.37 * m1).backward()
+
+    mu = ml[..., :L].clone().requires_grad_(True)
+    lv = ml[..., L:].clone().requires_grad_(True)
+    z2, e2, m2 = ops.reparam_kl(mu, lv, lens=lens, eps=eps, seed=99, offset=3, want_elem=True, want_mean=True)
+    ((z2.float() * gz.float()).sum() + (e2.float() * ge.float()).sum() + 0.37 * m2).backward()
+
+    assert torch.equal(z1, z2) and torch.equal(e1, e2) and torch.equal(m1, m2)
+    assert a.grad.shape == ml.shape
+    assert torch.equal(a.grad[..., :L], mu.grad) and torch.equal(a.grad[..., L:], lv.grad)
+
+
 @pytest.mark.parametrize("B,T,L", [(4, 30, 64), (2, 7, 5)])
 def test_reparam_kl_elem_gradient_path(cuda, B, T, L):
     """The reference module contract: unreduced 'loss' -> apply_lens_to_loss outside."""
