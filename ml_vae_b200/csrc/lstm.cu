@@ -721,10 +721,11 @@ using namespace mlvae;
 
 namespace {
 // A poll issued before the peers' words can have landed only loads the L2 (and every failed poll costs a ~600-cycle round trip):
-// the forward gate warps wait this many cycles after publishing h_t before their first poll.  Sweep on B200
-// (tests/probes/lstm_kernel_times.py 0 200 400 600 800 1000 1300): 0.838 / 0.837 / 0.812 / 0.785 / 0.801 / 0.842 / 0.938 ms
-// per 500-step forward launch; the backward kernel publishes at the very end of its step and gains nothing (1.107 ms at 0).
-int g_lstm_poll_delay_fwd = 600, g_lstm_poll_delay_bwd = 0;
+// the gate warps wait this many cycles after publishing before their first poll.  Sweeps on B200 (tests/probes/lstm_kernel_times.py,
+// ms per 500-step launch): forward 0 / 200 / 400 / 600 / 800 / 1000 / 1300 cycles -> 0.838 / 0.837 / 0.812 / 0.785 / 0.801 / 0.842 / 0.938;
+// backward (publishes at the very end of its step; in-warp reduce, no chain barrier) 0 / 300 / 500 / 700 / 900 -> 0.850 / 0.840 /
+// 0.837 / 0.865 / 0.895 (a second box: 0.972 / 0.965 / 0.938 at 0 / 300 / 500).
+int g_lstm_poll_delay_fwd = 600, g_lstm_poll_delay_bwd = 400;
 bool g_lstm_prof = false;        // a profile buffer is set: launch the instrumented instantiations
 struct LstmPlan {
     int slices, G;
