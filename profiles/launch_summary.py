@@ -22,6 +22,9 @@ e = starts[-back + 1] if back > 1 else len(rows)
 while s > 0 and ("Memset" in rows[s - 1][0] or "memset" in rows[s - 1][0]):
     s -= 1
 step = rows[s:e]
+# bench.py writes a 256 MiB buffer between timed steps (L2 flush, outside the event pairs): not part of the step
+flush = [r for r in step if "FillFunctor<unsigned char>" in r[0]]
+step = [r for r in step if "FillFunctor<unsigned char>" not in r[0]]
 agg = OrderedDict()
 for k, us in step:
     short = re.sub(r"\(.*", "", k).replace("void ", "").replace("(anonymous namespace)::", "")
@@ -30,6 +33,8 @@ for k, us in step:
     a[0] += us
     a[1] += 1
 tot = sum(us for _, us in step)
+if flush:
+    print(f"(excluded: {len(flush)} L2-flush fill of bench.py between steps, {sum(us for _, us in flush):.1f} us)")
 print(f"one training step: {len(step)} launches, sum of kernel durations {tot / 1e3:.3f} ms (serialised under ncu, cold caches)\n")
 for k, (us, n) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
     print(f"  {us:9.1f} us  {100 * us / tot:5.1f} %  x{n:<3d} {k}")
