@@ -222,6 +222,26 @@ int mlvae_global_norm(const float *d_x, const float *d_lens, int B, int T, int D
                       float *d_state, float *d_scratch, void *d_out, int out_dtype, void *stream);
 
 /* ------------------------------------------------------------------------- *
+ * Joint boundary / mispronunciation decoder (SURVEY 8f-4 "later"): the dynamic programme + backtrack of
+ * src/utils/decode_utils.py:440-548 (decode_plvl_md_lbl_seqs_full :374-565, same DP as _non_par :191-371), one CTA per
+ * utterance.  Inputs are the log-probability arrays the reference's pre-computation builds (decode_utils.py:421-438, float32):
+ *   d_log_p_yx (B, T, N, 2)  d_log_p_b (B, T, 2)  d_log_p_pi (B, T, 2)  d_log_p_y (N, 2)   finite or -inf, 8-byte aligned
+ *   d_y (B, Lmax) canonical phoneme indices in [0, N);  d_feat_lens / d_seq_lens (B) ABSOLUTE lengths T_b <= T, 1 <= L_b <= min(Lmax, T_b)
+ * Arithmetic is the reference's: float64 sums of the float32 terms in the order decode_utils.py:452-500 writes them, np.argmax's
+ * first-maximum rule, strict `>` for the final state.  numpy2 != 0: `weight * log_p_pi` and the first cell are float32 (numpy >= 2
+ * promotion, NEP 50); 0: float64 (numpy 1.x).  With weight == 1.0 only the first cell differs.
+ * Outputs (int32, -1 past the utterance's own length): d_boundary (B, T) 1 at the first frame of every phoneme,
+ * d_frames (B, T) frame-level labels (0 correct / 1 mispronounced), d_phones (B, Lmax) phoneme-level labels;
+ * d_status (B): 0 ok, 1 infeasible lengths (the reference fails its `assert l == t == 0`), 2 phoneme index out of range, 3 broken path.
+ * d_workspace: mlvae_md_decode_workspace_bytes(B, T, Lmax) bytes (0: back pointers fit in shared memory, pass NULL).  Lmax <= 1024.
+ * ------------------------------------------------------------------------- */
+size_t mlvae_md_decode_workspace_bytes(int B, int T, int Lmax);
+int mlvae_md_decode(const float *d_log_p_yx, const float *d_log_p_b, const float *d_log_p_pi, const float *d_log_p_y,
+                    const int32_t *d_y, const int32_t *d_feat_lens, const int32_t *d_seq_lens, int B, int T, int N, int Lmax,
+                    double weight, int numpy2, void *d_workspace, int32_t *d_boundary, int32_t *d_frames, int32_t *d_phones,
+                    int32_t *d_status, void *stream);
+
+/* ------------------------------------------------------------------------- *
  * Ragged PCM batch -> padded float32 matrix (replaces the host-side decode + pad of
  * src/utils/data_io.py:189-196 and the pickled feature cache of data_io.py:67-97 on the training path).
  * d_blob: the batch's utterances back to back, each start aligned to 8 samples (16 bytes for int16);

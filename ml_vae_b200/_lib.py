@@ -106,6 +106,8 @@ SIGNATURES = {
     "mlvae_mlp_chain_bwd_workspace_bytes": (_sz, [_i, _i, _i]),
     "mlvae_mlp_chain_bwd": (_i, [C.POINTER(ChainBwdArgs), _vp]),
     "mlvae_dropout": (_i, [_vp, _vp, _i64, C.c_float, _u64, _u64, _vp, _i, _vp]),
+    "mlvae_md_decode_workspace_bytes": (_sz, [_i, _i, _i]),
+    "mlvae_md_decode": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, C.c_double, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mlvae_fbank_fwd": (_i, [_vp, _vp, _vp, _i, _i64, _i64, _i, _vp, _i, _i, _vp, _vp, _vp]),
 }
 

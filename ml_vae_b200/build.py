@@ -17,7 +17,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libmlvae_b200.so")
 STAMP = LIB + ".stamp"
-SOURCES = ["latent_loss.cu", "fbank.cu", "norm.cu", "gemm_chain.cu", "dense_bwd.cu", "pcm.cu", "lstm.cu", "lstm_pack.cu", "dropout.cu", "gemm.cu", "optim.cu", "mlp_chain.cu", "dp_optim.cu"]
+SOURCES = ["latent_loss.cu", "fbank.cu", "norm.cu", "gemm_chain.cu", "dense_bwd.cu", "pcm.cu", "lstm.cu", "lstm_pack.cu", "dropout.cu", "gemm.cu", "optim.cu", "mlp_chain.cu", "dp_optim.cu", "md_decode.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default"]
 

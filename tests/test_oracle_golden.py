@@ -187,3 +187,27 @@ def test_front_end_pieces_agree_with_torchaudio():
     d_ours = fbank_ref.deltas(ours_db)
     d_ta = torchaudio.functional.compute_deltas(ours_db.transpose(1, 2), win_length=5, mode="replicate").transpose(1, 2)
     assert float((d_ours - d_ta).abs().max()) < 1e-12
+
+
+def test_decode_oracle_matches_reference_golden():
+    """oracle/decode_ref.py == the reference's decode_plvl_md_lbl_seqs_full (utils/decode_utils.py:374-565) on the vectors
+    oracle/gen_golden_decode.py produced by running the reference itself: three integer sequences per utterance, bit-exact."""
+    from oracle import decode_ref
+    g = np.load(os.path.join(GOLDEN, "md_decode_cases.npz"))
+    numpy2 = int(g["numpy_major"]) >= 2
+    assert int(g["n_cases"]) >= 4
+    for k in range(int(g["n_cases"])):
+        c = lambda n: g[f"c{k}.{n}"]
+        ob, of, op = decode_ref.decode_batch(c("log_p_yx"), c("log_p_b"), c("log_p_pi"), c("log_p_y"), c("y"), c("t_abs"), c("l_abs"),
+                                             weight=float(c("weight")), numpy2=numpy2)
+        for i in range(c("y").shape[0]):
+            Ti, Li = int(c("t_abs")[i]), int(c("l_abs")[i])
+            assert np.array_equal(ob[i], c("boundary")[i, :Ti])
+            assert list(of[i]) == list(c("frames")[i, :Ti]) and list(op[i]) == list(c("phones")[i, :Li])
+            assert int(ob[i].sum()) == Li and ob[i][0] == 1           # one boundary per phoneme, the first at frame 0
+    # the reference's clamp-then-log helper (decode_utils.py:8-14) on its corner values
+    x = np.array([0.0, 1e-6, 1e-5, 0.5, 1.0], dtype=np.float32)
+    assert np.allclose(decode_ref.ref_log(x), np.log(np.array([1e-5, 1e-5, 1e-5, 0.5, 1.0], dtype=np.float32)))
+    with pytest.raises(AssertionError):
+        decode_ref.decode_one(np.zeros((2, 3, 2), np.float32), np.zeros((2, 2), np.float32), np.zeros((2, 2), np.float32),
+                              np.zeros((3, 2), np.float32), np.array([0, 1, 2]))     # 3 phonemes, 2 frames
