@@ -454,6 +454,16 @@ int mlvae_lstm_fwd(void *d_p, const void *d_whh, void *d_y, float *d_c, int B, i
 int mlvae_lstm_bwd(void *d_gates, const float *d_c, const void *d_dy, const void *d_whh, float *d_bias_grad_part,
                    int B, int T, int H, void *d_scratch, void *stream);
 
+/* The same two kernels for ndir directions (2 = the calls above, 1 = a forward-only nn.LSTM(batch_first=True) layer: the main RNN
+ * of the MD_VAE* recipes, src/models/MD_VAE/model.yaml:78-83, and src/modules/boundary_detector.py:19, phoneme_recognizer.py:13):
+ * every "2" of the layouts above becomes ndir -- d_p / d_gates (B, T, ndir, H, 4), d_whh (ndir, 4H, H), d_y / d_c / d_dy (B, T, ndir*H),
+ * d_bias_grad_part (ceil(B/16), ndir, 4H).  One cooperative launch of (H/32) * ceil(B/16) * ndir CTAs (at most one per SM). */
+size_t mlvae_lstm_scratch_bytes_dirs(int B, int H, int ndir);
+int mlvae_lstm_fwd_dirs(void *d_p, const void *d_whh, void *d_y, float *d_c, int B, int T, int H, int ndir,
+                        int save_gates, void *d_scratch, void *stream);
+int mlvae_lstm_bwd_dirs(void *d_gates, const float *d_c, const void *d_dy, const void *d_whh, float *d_bias_grad_part,
+                        int B, int T, int H, int ndir, void *d_scratch, void *stream);
+
 /* Parameter plumbing of one bidirectional layer (nn.LSTM's parameters, modules/decoder.py:14-15): masters[8] / grads[8] =
  * {weight_ih, weight_hh, bias_ih, bias_hh} of the forward direction then of the _reverse one, float32 device pointers in
  * torch's (gate, unit) row order.  pack: -> bf16 W_ih (8H x In) with rows in the kernels' (direction, unit, gate) order,

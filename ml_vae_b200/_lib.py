@@ -82,6 +82,9 @@ SIGNATURES = {
     "mlvae_lstm_scratch_bytes": (_sz, [_i, _i]),
     "mlvae_lstm_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "mlvae_lstm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "mlvae_lstm_scratch_bytes_dirs": (_sz, [_i, _i, _i]),
+    "mlvae_lstm_fwd_dirs": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "mlvae_lstm_bwd_dirs": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "mlvae_norm_state_bytes": (_sz, [_i]),
     "mlvae_norm_scratch_bytes": (_sz, [_i, _i]),
     "mlvae_global_norm": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp]),

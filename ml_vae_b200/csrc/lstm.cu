@@ -116,17 +116,18 @@ __device__ long long *g_prof = nullptr;     // optional per-phase cycle counters
     long long *prof2 = (prof_on && warp == 0 && blockIdx.x == 0) ? g_prof + 12 : nullptr
 
 struct LstmFwdParams {
-    bf16 *P;                 // (B, T, 2, H, 4) gate pre-activations (unit-major, the 4 gates i,f,g,o adjacent) from the input projection;
+    bf16 *P;                 // (B, T, nd, H, 4) gate pre-activations (unit-major, the 4 gates i,f,g,o adjacent) from the input projection;
                              // overwritten with the ACTIVATED gates (i, f, g, o) when save != 0
-    const bf16 *Whh;         // (2, 4H, H)
-    bf16 *Y;                 // (B, T, 2H)
-    float *C;                // (B, T, 2H) cell states (saved for backward) or nullptr
+    const bf16 *Whh;         // (nd, 4H, H)
+    bf16 *Y;                 // (B, T, nd H)
+    float *C;                // (B, T, nd H) cell states (saved for backward) or nullptr
     uint4 *ll;               // [2 parity][groups][G producers][4 quarters][8 rows] zeroed words of 8 tagged bf16
     int B, T, H, save;
     int poll_delay;          // cycles between publishing h_t and the first poll for the group's h_t (see g_lstm_poll_delay)
+    int nd;                  // directions in the tensors' layout == gridDim.z == the kernel's kNd: 2 (bidirectional) or 1 (forward only)
 };
 
-template <bool kProf>
+template <bool kProf, int kNd>
 __global__ void __launch_bounds__(kLstmThreads, 1) lstm_fwd_kernel(LstmFwdParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t s_full[kChains][kIssuers], s_mma[kChains], s_free[kChains];
@@ -199,7 +200,7 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_fwd_kernel(LstmFwdParams
     tc::fence_after_sync();
 
     const uint32_t d_tile = tmem + dcol + chain * (kAcc * kMmaN);          // accumulator tile a at + a * kMmaN
-    const int groups = 2 * gridDim.y * kChains;
+    const int groups = kNd * gridDim.y * kChains;
     const int group = (d * gridDim.y + slice) * kChains + chain;
     const size_t ll_words = (size_t)G * 32;                                 // 16-byte words per group and parity
 
@@ -235,17 +236,18 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_fwd_kernel(LstmFwdParams
     } else if (active) {
         // ================= gate warps =================
         const int t_first = d ? (T - 1) : 0;
-        const ptrdiff_t p_step = (ptrdiff_t)(d ? -1 : 1) * 2 * H;           // P stride per time step in 8-byte units
-        const ptrdiff_t y_step = (ptrdiff_t)(d ? -1 : 1) * 2 * H;
+        constexpr int nd = kNd;                                              // directions in the tensors' layout (== gridDim.z)
+        const ptrdiff_t p_step = (ptrdiff_t)(d ? -1 : 1) * nd * H;          // P stride per time step in 8-byte units
+        const ptrdiff_t y_step = (ptrdiff_t)(d ? -1 : 1) * nd * H;
         const int my_row = part * 4 + gate;                                  // batch row this lane owns after the transpose
         const bool my_ok = (b0 + my_row) < B;
-        const size_t y_off = ((size_t)min(b0 + my_row, B - 1) * T + t_first) * (2 * H) + d * H + u * kUnits + unit_local;
+        const size_t y_off = ((size_t)min(b0 + my_row, B - 1) * T + t_first) * ((size_t)nd * H) + d * H + u * kUnits + unit_local;
         bf16 *pY = p.Y + y_off;
         float *pC = p.C ? p.C + y_off : nullptr;
         // gate buffer layout: (B, T, 2, H, 4) -- the four gates of a unit are adjacent, so the lane that owns (unit, batch
         // row) after the transpose reads its pre-activations and writes its activated gates with ONE 8-byte access
         uint2 *pG = reinterpret_cast<uint2 *>(p.P) +
-                    (((size_t)min(b0 + my_row, B - 1) * T + t_first) * 2 + d) * (size_t)H + u * kUnits + unit_local;
+                    (((size_t)min(b0 + my_row, B - 1) * T + t_first) * nd + d) * (size_t)H + u * kUnits + unit_local;
         // this warp's eight units of batch row my_row are one exchange word: producer u, row my_row, quarter q
         // exchange layout per group and parity: 16-byte word (producer, quarter, row) at (producer * 4 + quarter) * 8 + row, element e of
         // the word = unit 8 * quarter + e.  Every lane publishes its own 2 bytes: a warp (8 units x rows part*4 .. +3 of its quarter)
@@ -391,14 +393,15 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_fwd_kernel(LstmFwdParams
 //            CTAs that own the units
 // ======================================================================================
 struct LstmBwdParams {
-    bf16 *G;                 // (B, T, 2, H, 4) in: activated gates from the forward pass; out: pre-activation grads
+    bf16 *G;                 // (B, T, nd, H, 4) in: activated gates from the forward pass; out: pre-activation grads
     const float *C;          // (B, T, 2H) cell states from the forward pass
     const bf16 *dY;          // (B, T, 2H) gradient of the layer output
     const bf16 *Whh;         // (2, 4H, H)
     uint4 *ll;               // [2 parity][groups][G owners][8 unit quads][G producers][4 units] zeroed 16-byte words = 8 rows of tagged bf16
-    float *db_part;          // (slices, 2, 4H) per-16-row-slice sums over (rows, t) of dA, torch gate order; or nullptr
+    float *db_part;          // (slices, nd, 4H) per-16-row-slice sums over (rows, t) of dA, torch gate order; or nullptr
     int B, T, H;
     int poll_delay;
+    int nd;                  // directions (see LstmFwdParams)
 };
 
 constexpr float kWireUnscale = 18446744073709551616.f;    // 2^64
@@ -416,7 +419,7 @@ __device__ __forceinline__ uint32_t wire_pack(float x0, float x1, uint32_t tag) 
     return (*reinterpret_cast<const uint32_t *>(&pk) & ~kTagBits) | tag;
 }
 
-template <bool kProf>
+template <bool kProf, int kNd>
 __global__ void __launch_bounds__(kLstmThreads, 1) lstm_bwd_kernel(LstmBwdParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t s_da[kChains][2], s_mma[kChains], s_free[kChains];
@@ -486,7 +489,7 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_bwd_kernel(LstmBwdParams
     __syncthreads();
     tc::fence_after_sync();
 
-    const int groups = 2 * gridDim.y * kChains;
+    const int groups = kNd * gridDim.y * kChains;
     const int group = (d * gridDim.y + slice) * kChains + chain;
     const size_t ll_words = (size_t)G * G * 32;                                      // 16-byte words per group and parity
     const uint32_t d_tile0 = tmem + dcol + chain * 4 * kMmaN;
@@ -537,10 +540,11 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_bwd_kernel(LstmBwdParams
         uint2 *G2 = reinterpret_cast<uint2 *>(p.G);
         const unsigned short *dY16 = reinterpret_cast<const unsigned short *>(p.dY);
         const int t_first = d ? 0 : (T - 1);
-        const ptrdiff_t g_step = (ptrdiff_t)(d ? 1 : -1) * 2 * H;
-        const ptrdiff_t y_step = (ptrdiff_t)(d ? 1 : -1) * 2 * H;
-        size_t g_off = (((size_t)b * T + t_first) * 2 + d) * (size_t)H + u * kUnits + unit;        // 8-byte units: (B,T,2,H,4)
-        size_t y_off = ((size_t)b * T + t_first) * (2 * H) + d * H + u * kUnits + unit;
+        constexpr int nd = kNd;                                              // directions in the tensors' layout (== gridDim.z)
+        const ptrdiff_t g_step = (ptrdiff_t)(d ? 1 : -1) * nd * H;
+        const ptrdiff_t y_step = (ptrdiff_t)(d ? 1 : -1) * nd * H;
+        size_t g_off = (((size_t)b * T + t_first) * nd + d) * (size_t)H + u * kUnits + unit;       // 8-byte units: (B,T,nd,H,4)
+        size_t y_off = ((size_t)b * T + t_first) * ((size_t)nd * H) + d * H + u * kUnits + unit;
         // consumer identity: lane pulls the sector of producer lane % 16, units 4 gw + 2 (lane / 16), + 1: the 16 producers of a unit
         // pair are the 16 lanes of a half warp
         const int c_pr = lane & 15, c_u0 = 4 * gw + 2 * (lane >> 4);
@@ -708,7 +712,7 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_bwd_kernel(LstmBwdParams
             float acc = 0.f;
 #pragma unroll
             for (int r = 0; r < kChains * kGateWarps; ++r) acc += s_b[(r * 4 + g) * 32 + un];
-            p.db_part[((size_t)slice * 2 + d) * 4 * H + (size_t)g * H + u * kUnits + un] = acc;
+            p.db_part[((size_t)slice * kNd + d) * 4 * H + (size_t)g * H + u * kUnits + un] = acc;
         }
     }
     if (warp == 0) tc::tmem_dealloc(tmem, tmem_cols);
@@ -731,15 +735,16 @@ struct LstmPlan {
     int slices, G;
     size_t smem_fwd, smem_bwd, ll_fwd, ll_bwd;
 };
-int lstm_plan(int B, int H, LstmPlan &pl) {
+int lstm_plan(int B, int H, int nd, LstmPlan &pl) {
     MLVAE_REQUIRE(H % 32 == 0 && H >= 32 && H <= 512, MLVAE_ERR_UNSUPPORTED,
                   "lstm: hidden size must be a multiple of 32 in [32, 512] (W_hh slice resident in tensor memory), got %d", H);
+    MLVAE_REQUIRE(nd == 1 || nd == 2, MLVAE_ERR_INVALID_ARG, "lstm: 1 or 2 directions, got %d", nd);
     pl.G = H / kUnits;
     const int sms = sm_count();
     pl.slices = (B + kChains * kChainRows - 1) / (kChains * kChainRows);          // 16 batch rows (two 8-row chains) per CTA
-    MLVAE_REQUIRE((int64_t)pl.G * pl.slices * 2 <= sms, MLVAE_ERR_UNSUPPORTED,
-                  "lstm: batch %d x hidden %d needs %d co-resident CTAs (> %d SMs)", B, H, pl.G * pl.slices * 2, sms);
-    const size_t groups = (size_t)2 * pl.slices * kChains;
+    MLVAE_REQUIRE((int64_t)pl.G * pl.slices * nd <= sms, MLVAE_ERR_UNSUPPORTED,
+                  "lstm: batch %d x hidden %d x %d direction(s) needs %d co-resident CTAs (> %d SMs)", B, H, nd, pl.G * pl.slices * nd, sms);
+    const size_t groups = (size_t)nd * pl.slices * kChains;
     pl.smem_fwd = (size_t)kChains * kMmaN * H * 2;
     pl.smem_bwd = (size_t)kChains * kMmaN * 128 * 2;                                // dA tiles = 8 KB (also holds the bias reduction's 8 KB)
     pl.ll_fwd = 2 * groups * pl.G * 32 * sizeof(uint4);
@@ -767,45 +772,58 @@ int mlvae_debug_set_option(int key, int value) {
 }
 
 // Scratch: the tagged exchange words, zeroed by every call.
-size_t mlvae_lstm_scratch_bytes(int B, int H) {
+size_t mlvae_lstm_scratch_bytes_dirs(int B, int H, int ndir) {
     LstmPlan pl;
-    if (B <= 0 || lstm_plan(B, H, pl) != MLVAE_OK) return 0;
+    if (B <= 0 || lstm_plan(B, H, ndir, pl) != MLVAE_OK) return 0;
     return (pl.ll_fwd > pl.ll_bwd ? pl.ll_fwd : pl.ll_bwd) + 256;
 }
+size_t mlvae_lstm_scratch_bytes(int B, int H) { return mlvae_lstm_scratch_bytes_dirs(B, H, 2); }
 
-int mlvae_lstm_fwd(void *d_p, const void *d_whh, void *d_y, float *d_c, int B, int T, int H, int save_gates,
-                   void *d_scratch, void *stream) {
+int mlvae_lstm_fwd_dirs(void *d_p, const void *d_whh, void *d_y, float *d_c, int B, int T, int H, int ndir, int save_gates,
+                        void *d_scratch, void *stream) {
     MLVAE_REQUIRE(d_p && d_whh && d_y && d_scratch, MLVAE_ERR_INVALID_ARG, "lstm_fwd: missing buffers");
     MLVAE_REQUIRE(B > 0 && T > 0 && H > 0 && T < (1 << 30), MLVAE_ERR_INVALID_ARG, "lstm_fwd: bad sizes");
     MLVAE_REQUIRE(((uintptr_t)d_scratch & 31) == 0, MLVAE_ERR_INVALID_ARG, "lstm_fwd: scratch must be 32-byte aligned");
     LstmPlan pl;
-    if (int rc = lstm_plan(B, H, pl)) return rc;
+    if (int rc = lstm_plan(B, H, ndir, pl)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     MLVAE_CHECK_CUDA(cudaMemsetAsync(d_scratch, 0, pl.ll_fwd, st));
-    LstmFwdParams prm{(bf16 *)d_p, (const bf16 *)d_whh, (bf16 *)d_y, d_c, (uint4 *)d_scratch, B, T, H, save_gates, g_lstm_poll_delay_fwd};
+    LstmFwdParams prm{(bf16 *)d_p, (const bf16 *)d_whh, (bf16 *)d_y, d_c, (uint4 *)d_scratch, B, T, H, save_gates, g_lstm_poll_delay_fwd, ndir};
     void *args[] = {&prm};
-    dim3 grid(pl.G, pl.slices, 2), block(kLstmThreads);
-    const void *fn = g_lstm_prof ? (const void *)lstm_fwd_kernel<true> : (const void *)lstm_fwd_kernel<false>;
+    dim3 grid(pl.G, pl.slices, ndir), block(kLstmThreads);
+    const void *fn = ndir == 2 ? (g_lstm_prof ? (const void *)lstm_fwd_kernel<true, 2> : (const void *)lstm_fwd_kernel<false, 2>)
+                               : (g_lstm_prof ? (const void *)lstm_fwd_kernel<true, 1> : (const void *)lstm_fwd_kernel<false, 1>);
     MLVAE_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_fwd));
     MLVAE_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, grid, block, args, pl.smem_fwd, st));
     return MLVAE_OK;
 }
 
-int mlvae_lstm_bwd(void *d_gates, const float *d_c, const void *d_dy, const void *d_whh, float *d_bias_grad_part, int B, int T,
-                   int H, void *d_scratch, void *stream) {
+int mlvae_lstm_fwd(void *d_p, const void *d_whh, void *d_y, float *d_c, int B, int T, int H, int save_gates,
+                   void *d_scratch, void *stream) {
+    return mlvae_lstm_fwd_dirs(d_p, d_whh, d_y, d_c, B, T, H, 2, save_gates, d_scratch, stream);
+}
+
+int mlvae_lstm_bwd_dirs(void *d_gates, const float *d_c, const void *d_dy, const void *d_whh, float *d_bias_grad_part, int B, int T,
+                        int H, int ndir, void *d_scratch, void *stream) {
     MLVAE_REQUIRE(d_gates && d_c && d_dy && d_whh && d_scratch, MLVAE_ERR_INVALID_ARG, "lstm_bwd: missing buffers");
     MLVAE_REQUIRE(B > 0 && T > 0 && H > 0 && T < (1 << 30), MLVAE_ERR_INVALID_ARG, "lstm_bwd: bad sizes");
     MLVAE_REQUIRE(((uintptr_t)d_scratch & 31) == 0, MLVAE_ERR_INVALID_ARG, "lstm_bwd: scratch must be 32-byte aligned");
     LstmPlan pl;
-    if (int rc = lstm_plan(B, H, pl)) return rc;
+    if (int rc = lstm_plan(B, H, ndir, pl)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     MLVAE_CHECK_CUDA(cudaMemsetAsync(d_scratch, 0, pl.ll_bwd, st));
-    LstmBwdParams prm{(bf16 *)d_gates, d_c, (const bf16 *)d_dy, (const bf16 *)d_whh, (uint4 *)d_scratch, d_bias_grad_part, B, T, H, g_lstm_poll_delay_bwd};
+    LstmBwdParams prm{(bf16 *)d_gates, d_c, (const bf16 *)d_dy, (const bf16 *)d_whh, (uint4 *)d_scratch, d_bias_grad_part, B, T, H, g_lstm_poll_delay_bwd, ndir};
     void *args[] = {&prm};
-    dim3 grid(pl.G, pl.slices, 2), block(kLstmThreads);
-    const void *fn = g_lstm_prof ? (const void *)lstm_bwd_kernel<true> : (const void *)lstm_bwd_kernel<false>;
+    dim3 grid(pl.G, pl.slices, ndir), block(kLstmThreads);
+    const void *fn = ndir == 2 ? (g_lstm_prof ? (const void *)lstm_bwd_kernel<true, 2> : (const void *)lstm_bwd_kernel<false, 2>)
+                               : (g_lstm_prof ? (const void *)lstm_bwd_kernel<true, 1> : (const void *)lstm_bwd_kernel<false, 1>);
     MLVAE_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, grid, block, args, pl.smem_bwd, st));
     return MLVAE_OK;
+}
+
+int mlvae_lstm_bwd(void *d_gates, const float *d_c, const void *d_dy, const void *d_whh, float *d_bias_grad_part, int B, int T,
+                   int H, void *d_scratch, void *stream) {
+    return mlvae_lstm_bwd_dirs(d_gates, d_c, d_dy, d_whh, d_bias_grad_part, B, T, H, 2, d_scratch, stream);
 }
 
 }  // extern "C"

@@ -335,3 +335,117 @@ def bilstm_layer(x, w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh
     guarantees one of the two happens before the gradients are read (Decoder: every layer but the lowest; TrainStep flushes)."""
     return _BiLSTMLayer.apply(x.contiguous(), w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r, training,
                               direct_grads, after_recurrence, input_dropout, defer_weight_grads)
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# Forward-only layer: nn.LSTM(batch_first=True) without `bidirectional` -- the main RNN of the MD_VAE* recipes
+# (models/MD_VAE/model.yaml:78-83), modules/boundary_detector.py:19, modules/phoneme_recognizer.py:13.  Same two recurrence kernels
+# (their one-direction instantiation, mlvae_lstm_fwd_dirs / _bwd_dirs with ndir = 1) and the same GEMM for the time-parallel
+# products; the parameter plumbing (cast / gate-row permutation of four small tensors) is left to torch here.
+# ------------------------------------------------------------------------------------------------------------------------------
+def max_rows_per_launch_dirs(hidden: int, device, ndir: int) -> int:
+    sms = torch.cuda.get_device_properties(device).multi_processor_count
+    return max(16, (sms // (ndir * (hidden // 32))) * 16)
+
+
+def supported_uni(x: torch.Tensor, hidden: int) -> bool:
+    return x.is_cuda and x.dtype == torch.bfloat16 and hidden % 32 == 0 and 32 <= hidden <= 512 and x.shape[-1] % 8 == 0 \
+        and L.lib().mlvae_lstm_scratch_bytes_dirs(min(x.shape[0], max_rows_per_launch_dirs(hidden, x.device, 1)), hidden, 1) > 0
+
+
+def _scratch_dirs(B, H, ndir, device):
+    need = L.lib().mlvae_lstm_scratch_bytes_dirs(B, H, ndir)
+    if need == 0:
+        raise L.MlvaeError(f"persistent LSTM does not support batch {B} x hidden {H}: {L.lib().mlvae_last_error().decode()}")
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    buf = _scratch.get(key)
+    if buf is None or buf.numel() < need:
+        buf = torch.empty(need, dtype=torch.uint8, device=device)
+        _scratch[key] = buf
+    return buf
+
+
+class _UniLSTMLayer(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w_ih, w_hh, b_ih, b_hh, training, input_dropout):
+        from .gemm import gemm
+        B, T, In = x.shape
+        H = w_hh.shape[1]
+        H4 = 4 * H
+        bf, dev = torch.bfloat16, x.device
+        if not _gemm_ok(In, H, x):
+            raise NotImplementedError(f"lstm_layer: input size {In} / hidden size {H} must be multiples of 8 (16-byte rows for TMA)")
+        if input_dropout is not None:
+            p_drop, d_seed, d_off, d_dev = input_dropout
+            xd = torch.empty_like(x)
+            L.check(L.lib().mlvae_dropout(L.ptr(x), L.ptr(xd), x.numel(), float(p_drop), d_seed, d_off, L.ptr(d_dev), L.BF16, L.stream_ptr()),
+                    "mlvae_dropout")
+            x = xd
+        x2 = x.reshape(B * T, In)
+        perm = _gate_perm(H, dev)[0][:H4]                                  # kernel row unit*4+gate <- torch row gate*H+unit
+        w_ih_p = w_ih.to(bf)[perm].contiguous()
+        w_hh_b = w_hh.to(bf).contiguous().view(1, H4, H)                   # torch row order (the kernels index it by gate*H+unit)
+        bias_p = (b_ih + b_hh).float()[perm].contiguous()
+        P = torch.empty(B, T, 1, H4, dtype=bf, device=dev)
+        gemm(x2, w_ih_p, P, B * T, H4, In, lda=In, ldb=In, ldd=H4, bias=bias_p)
+        y = torch.empty(B, T, H, dtype=bf, device=dev)
+        c = torch.empty(B, T, H, dtype=torch.float32, device=dev) if training else None
+        rows = max_rows_per_launch_dirs(H, dev, 1)
+        for b0 in range(0, B, rows):
+            b1 = min(B, b0 + rows)
+            L.check(L.lib().mlvae_lstm_fwd_dirs(L.ptr(P[b0:b1]), L.ptr(w_hh_b), L.ptr(y[b0:b1]), L.ptr(c[b0:b1]) if training else None,
+                                                b1 - b0, T, H, 1, int(training), L.ptr(_scratch_dirs(b1 - b0, H, 1, dev)), L.stream_ptr()),
+                    "mlvae_lstm_fwd_dirs")
+        ctx.input_dropout = input_dropout
+        if training:
+            ctx.save_for_backward(x, w_ih_p, w_hh_b, P, c, y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        from .gemm import gemm
+        x, w_ih_p, w_hh_b, gates, c, y = ctx.saved_tensors
+        if getattr(ctx, "consumed", False):
+            raise RuntimeError("lstm_layer: backward called twice over the same forward; the saved gate buffer is consumed by the "
+                               "first backward -- run the forward again")
+        ctx.consumed = True
+        B, T, In = x.shape
+        H = w_hh_b.shape[2]
+        H4, dev = 4 * H, x.device
+        dy = dy.contiguous().to(torch.bfloat16)
+        rows = max_rows_per_launch_dirs(H, dev, 1)
+        n_slices = sum((min(B, b0 + rows) - b0 + 15) // 16 for b0 in range(0, B, rows))
+        db_part = torch.empty(n_slices, H4, dtype=torch.float32, device=dev)
+        part0 = 0
+        for b0 in range(0, B, rows):
+            b1 = min(B, b0 + rows)
+            L.check(L.lib().mlvae_lstm_bwd_dirs(L.ptr(gates[b0:b1]), L.ptr(c[b0:b1]), L.ptr(dy[b0:b1]), L.ptr(w_hh_b), L.ptr(db_part[part0:]),
+                                                b1 - b0, T, H, 1, L.ptr(_scratch_dirs(b1 - b0, H, 1, dev)), L.stream_ptr()), "mlvae_lstm_bwd_dirs")
+            part0 += (b1 - b0 + 15) // 16
+        dA2 = gates.view(B * T, H4)                                         # pre-activation gradients, columns in (unit, gate) order
+        x2, y2 = x.reshape(B * T, In), y.view(B * T, H)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(B, T, In, dtype=torch.bfloat16, device=dev)
+            kw = {}
+            if ctx.input_dropout is not None:
+                p_drop, d_seed, d_off, d_dev = ctx.input_dropout
+                kw = dict(drop_p=p_drop, drop_seed=d_seed, drop_offset=d_off, drop_offset_dev=d_dev)
+            gemm(dA2, w_ih_p, dx, B * T, In, H4, lda=H4, ldb=In, ldd=In, b_mn=True, **kw)
+        g_ih = torch.empty(H4, In, dtype=torch.float32, device=dev)
+        g_hh = torch.zeros(H4, H, dtype=torch.float32, device=dev)
+        tiles = ((H4 + 127) // 128) * ((In + 255) // 256)
+        gemm([dA2], [x2], [g_ih], H4, In, B * T, lda=H4, ldb=In, ldd=In, a_mn=True, b_mn=True, out_f32=True, row_perm_H=H,
+             split_k=1 if tiles >= 96 else max(1, min(8, 128 // tiles)))
+        if T > 1:
+            # dW_hh = sum_b sum_t dA[b, t+1]^T h[b, t]: one batched GEMM over row-shifted views (TMA zero-fills past T-1 rows)
+            tiles = ((H4 + 127) // 128) * ((H + 255) // 256)
+            gemm([dA2[1:]], [y2], [g_hh], H4, H, T - 1, lda=H4, ldb=H, ldd=H, a_mn=True, b_mn=True, kbatches=B, a_batch_stride=T * H4,
+                 b_batch_stride=T * H, out_f32=True, row_perm_H=H, split_k=1 if tiles >= 96 else max(1, min(4, 128 // tiles)))
+        db = db_part.sum(0)                                                 # torch gate order already; both biases get it
+        return dx, g_ih, g_hh, db, db.clone(), None, None
+
+
+def lstm_layer(x, w_ih, w_hh, b_ih, b_hh, training: bool, input_dropout=None):
+    """One forward-direction LSTM layer with torch's parameters (float32 masters): x (B, T, In) bf16 -> (B, T, H) bf16."""
+    return _UniLSTMLayer.apply(x.contiguous(), w_ih, w_hh, b_ih, b_hh, training, input_dropout)

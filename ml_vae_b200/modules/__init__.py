@@ -5,3 +5,4 @@ from .vanilla_vae import VanillaVAE  # noqa: F401
 from .decoder import Decoder  # noqa: F401
 from .gmm_vae import GMMVAE  # noqa: F401
 from .h_vae import HierarchicalVAE  # noqa: F401
+from .lstm import LSTM  # noqa: F401
