@@ -440,6 +440,8 @@ int mlvae_dropout(const void *d_x, void *d_y, int64_t n, float p, uint64_t seed,
 size_t mlvae_lstm_scratch_bytes(int B, int H);
 /* debug: 8 zeroed int64 device counters receiving per-phase cycle totals of CTA 0; NULL disables */
 int mlvae_debug_set_profile_buffer(void *d_prof);
+/* debug: 4*T zeroed int32 device words receiving the four phase durations (cycles) of every step of one gate warp; NULL disables */
+int mlvae_debug_set_trace_buffer(void *d_trace);
 /* debug / tuning knobs: key 1 = MMA issuer warps of the LSTM kernels (1, 2, 4) */
 int mlvae_debug_set_option(int key, int value);
 int mlvae_lstm_fwd(void *d_p, const void *d_whh, void *d_y, float *d_c, int B, int T, int H,

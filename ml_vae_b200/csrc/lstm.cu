@@ -97,12 +97,15 @@ __device__ __forceinline__ bool tag_ok(const u32x8 &w, uint32_t tag) {      // a
 __device__ __forceinline__ uint4 untag(const uint4 &w) { return make_uint4(w.x & ~kTagBits, w.y & ~kTagBits, w.z & ~kTagBits, w.w & ~kTagBits); }
 
 __device__ long long *g_prof = nullptr;     // optional per-phase cycle counters (debug / profiles/)
+__device__ int *g_trace = nullptr;          // optional per-STEP phase cycles of gate warp 0 / chain 0 / CTA (0,0,0): int[4 * T] (instrumented build)
 // phase time stamps of ONE thread, accumulated in registers and written once at the end (a global read-modify-write per
 // mark would put an L2 round trip into every phase)
 // (the kernels are instantiated with and without the instrumentation: kProf = false compiles all of it away)
 #define PROF_MARK(k)                                                     \
     do {                                                                 \
-        if constexpr (kProf) { if (prof) { const long long now = clock64(); pacc[k] += now - tprev; tprev = now; } } \
+        if constexpr (kProf) { if (prof) { const long long now = clock64(); pacc[k] += now - tprev;                 \
+            if (g_trace && prof == g_prof) g_trace[4 * step + (k)] = (int)(now - tprev);                             \
+            tprev = now; } }                                                                                         \
     } while (0)
 #define PROF_FLUSH()                                                     \
     do {                                                                 \
@@ -760,6 +763,14 @@ int mlvae_debug_set_profile_buffer(void *d_prof) {
     long long *ptr = (long long *)d_prof;
     MLVAE_CHECK_CUDA(cudaMemcpyToSymbol(g_prof, &ptr, sizeof(ptr)));
     g_lstm_prof = ptr != nullptr;
+    return MLVAE_OK;
+}
+
+// Debug: d_trace = 4 * T ints receiving the four phase durations of EVERY step of gate warp 0, chain 0, CTA (0,0,0) (needs a profile
+// buffer as well: the instrumented instantiation); NULL disables.
+int mlvae_debug_set_trace_buffer(void *d_trace) {
+    int *ptr = (int *)d_trace;
+    MLVAE_CHECK_CUDA(cudaMemcpyToSymbol(g_trace, &ptr, sizeof(ptr)));
     return MLVAE_OK;
 }
 
