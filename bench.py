@@ -376,6 +376,15 @@ def run_ours(args):
     lstm_mod.PROBE = None
     gemm_evs = [(f, a.elapsed_time(b)) for f, a, b in (gemm_mod.PROBE or [])]
     gemm_mod.PROBE = None
+    # data parallel: the step is paced by the slowest rank (max over ranks); the recurrence kernels are the part of the step whose
+    # duration differs from GPU to GPU, so every rank's own median goes into the line
+    per_rank_lstm = None
+    if world > 1:
+        med = lambda v: sorted(v)[len(v) // 2] if v else float("nan")
+        mine = torch.tensor([med(lstm_ms.get("lstm_fwd", [])), med(lstm_ms.get("lstm_bwd", []))], device=dev, dtype=torch.float64)
+        allv = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allv, mine)
+        per_rank_lstm = {"lstm_fwd_ms": [round(float(v[0]), 4) for v in allv], "lstm_bwd_ms": [round(float(v[1]), 4) for v in allv]}
 
     e2e_steps = [max(1, args.warmup // 2)]
     for i in range(e2e_steps[0]):
@@ -458,6 +467,10 @@ def run_ours(args):
             line["config"]["parallelism"] += " (peer-memory reduce-scatter / sharded Adam / all-gather)"
         else:
             line["data_parallel"] = {"mode": "nccl", "kernels": "ncclAllReduce of the flat gradient bucket + adam_step_kernel on every rank"}
+        if per_rank_lstm:
+            line["data_parallel"]["per_rank_median_ms_per_launch"] = per_rank_lstm
+            line["data_parallel"]["note"] = ("the step time is the max over ranks; 4 recurrence launches per step, so a rank whose lstm_bwd "
+                                             "launch is 0.1 ms slower than rank 0's paces every rank 0.2 ms slower")
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             v, dt, cores = time_cpu_reference(B, 3, 1)
