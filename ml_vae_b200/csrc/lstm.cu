@@ -79,7 +79,11 @@ __device__ __forceinline__ u32x8 ld_volatile_u8(const uint4 *p) {
     return v;
 }
 __device__ __forceinline__ void st_volatile_u4(uint4 *p, uint4 v) {
+#ifdef MLVAE_LSTM_WEAK_ST
+    asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+#else
     asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+#endif
 }
 __device__ __forceinline__ void st_volatile_u16(unsigned short *p, unsigned short v) {
     asm volatile("st.relaxed.gpu.global.u16 [%0], %1;" ::"l"(p), "h"(v) : "memory");
@@ -731,8 +735,10 @@ namespace {
 // the gate warps wait this many cycles after publishing before their first poll.  Sweeps on B200 (tests/probes/lstm_kernel_times.py,
 // ms per 500-step launch): forward 0 / 200 / 400 / 600 / 800 / 1000 / 1300 cycles -> 0.838 / 0.837 / 0.812 / 0.785 / 0.801 / 0.842 / 0.938;
 // backward (publishes at the very end of its step; in-warp reduce, no chain barrier) 0 / 300 / 500 / 700 / 900 -> 0.850 / 0.840 /
-// 0.837 / 0.865 / 0.895 (a second box: 0.972 / 0.965 / 0.938 at 0 / 300 / 500).
-int g_lstm_poll_delay_fwd = 600, g_lstm_poll_delay_bwd = 400;
+// 0.837 / 0.865 / 0.895 (a second box: 0.972 / 0.965 / 0.938 at 0 / 300 / 500).  GPUs of the pool fall into two classes for the backward
+// kernel (profiles/r02_per_gpu_spread.txt): 0.83-0.84 ms at 400 and +2 % at 600 on most, 0.91-0.92 ms at 400 and -1.5 % at 600 on the
+// others (less L2 request head-room: they also lose 4 % with the half-line polling layout MLVAE_LSTM_BWD_LAYOUT_V1); 500 suits both.
+int g_lstm_poll_delay_fwd = 600, g_lstm_poll_delay_bwd = 500;
 bool g_lstm_prof = false;        // a profile buffer is set: launch the instrumented instantiations
 struct LstmPlan {
     int slices, G;
