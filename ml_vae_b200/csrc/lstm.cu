@@ -79,11 +79,7 @@ __device__ __forceinline__ u32x8 ld_volatile_u8(const uint4 *p) {
     return v;
 }
 __device__ __forceinline__ void st_volatile_u4(uint4 *p, uint4 v) {
-#ifdef MLVAE_LSTM_WEAK_ST
-    asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-#else
     asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-#endif
 }
 __device__ __forceinline__ void st_volatile_u16(unsigned short *p, unsigned short v) {
     asm volatile("st.relaxed.gpu.global.u16 [%0], %1;" ::"l"(p), "h"(v) : "memory");
