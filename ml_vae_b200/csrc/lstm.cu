@@ -84,7 +84,6 @@ __device__ __forceinline__ void st_volatile_u4(uint4 *p, uint4 v) {
 __device__ __forceinline__ void st_volatile_u16(unsigned short *p, unsigned short v) {
     asm volatile("st.relaxed.gpu.global.u16 [%0], %1;" ::"l"(p), "h"(v) : "memory");
 }
-__device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
 // tag in bit 14 of every bf16 of the exchange words
 constexpr uint32_t kTagBits = 0x40004000u;
@@ -550,7 +549,7 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_bwd_kernel(LstmBwdParams
         size_t y_off = ((size_t)b * T + t_first) * ((size_t)nd * H) + d * H + u * kUnits + unit;
         // consumer identity: lane pulls the sector of producer lane % 16, units 4 gw + 2 (lane / 16), + 1: the 16 producers of a unit
         // pair are the 16 lanes of a half warp
-        const int c_pr = lane & 15, c_u0 = 4 * gw + 2 * (lane >> 4);
+        const int c_pr = lane & 15;
         const bool c_has = c_pr < G;
         // producer identity: the warps with part == 0 ship the M-tiles 0, 1 and those with part == 1 the tiles 2, 3, each thread ALL
         // eight rows of unit `lane` of owner 4m+q: one 16-byte word per thread, 512 contiguous bytes (16 whole sectors) per warp store
@@ -562,8 +561,8 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_bwd_kernel(LstmBwdParams
         // a producer warp store covers 8 x 64 contiguous bytes (whole sectors)
         const size_t src_o = (((size_t)u * 8 + gw) * G + (c_has ? c_pr : 0)) * 4 + 2 * (lane >> 4);
         const size_t dst_o = ((size_t)(lane >> 2) * G + u) * 4 + (lane & 3);       // + owner * G * 32
-#else
-        const size_t src_o = (size_t)u * G * 32 + (size_t)(c_has ? c_pr : 0) * 32 + c_u0, dst_o = (size_t)u * 32 + lane;
+#else      // producer-major layout [owner][producer][unit] (A/B only: 16 half lines per poll; 4 % slower on the GPUs with less L2 request head-room)
+        const size_t src_o = (size_t)u * G * 32 + (size_t)(c_has ? c_pr : 0) * 32 + 4 * gw + 2 * (lane >> 4), dst_o = (size_t)u * 32 + lane;
 #endif
         const uint4 *const src0 = base0 + src_o, *const src1 = base1 + src_o;
         uint4 *const dst0 = base0 + dst_o, *const dst1 = base1 + dst_o;       // + owner * G * 32
