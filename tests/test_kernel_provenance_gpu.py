@@ -54,3 +54,27 @@ def test_fp32_step_is_a_library_validation_path(cuda):
     assert "lstm_fwd_kernel" not in joined and "gemm_bf16_kernel" not in joined
     for must in ("reparam_kl_fwd_kernel", "recon_fwd_kernel", "logmel", "adam_step_kernel"):      # the repo kernels the fp32 tests DO cover
         assert must in joined, must
+
+
+def test_lstm_module_and_decoder_run_on_repo_kernels(cuda):
+    """The torch.nn.LSTM drop-in (forward-only, bf16) launches the one-direction recurrence instantiation and the TMA GEMM, no cuDNN /
+    cuBLAS kernel; the label decoder is one md_decode_kernel launch."""
+    from torch.profiler import ProfilerActivity, profile
+    from ml_vae_b200.modules import LSTM
+    from ml_vae_b200.utils import decode_utils as du
+    m = LSTM(128, 256, 2, batch_first=True, dropout=0.15).to(cuda).train()
+    x = torch.randn(8, 40, 128, device=cuda).bfloat16().requires_grad_(True)
+    m(x)[0].float().sum().backward()
+    logs = [torch.log(torch.rand(s, device=cuda).clamp_min(1e-5)) for s in ((4, 30, 9, 2), (4, 30, 2), (4, 30, 2), (9, 2))]
+    y = torch.randint(0, 9, (4, 6), device=cuda)
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        m(x)[0].float().sum().backward()
+        du.decode_from_logs(*logs, y, torch.full((4,), 30), torch.full((4,), 6), device=cuda)
+        torch.cuda.synchronize()
+    names = [e.key for e in prof.key_averages()]
+    lib = [n for n in names if any(k in n for k in LIBRARY_MARKERS)]
+    assert not lib, lib
+    joined = " ".join(names)
+    for must in ("lstm_fwd_kernel", "lstm_bwd_kernel", "gemm_bf16_kernel", "dropout_kernel", "md_decode_kernel"):
+        assert must in joined, must
