@@ -397,6 +397,7 @@ class _UniLSTMLayer(torch.autograd.Function):
                                                 b1 - b0, T, H, 1, int(training), L.ptr(_scratch_dirs(b1 - b0, H, 1, dev)), L.stream_ptr()),
                     "mlvae_lstm_fwd_dirs")
         ctx.input_dropout = input_dropout
+        ctx.param_dtype = w_ih.dtype
         if training:
             ctx.save_for_backward(x, w_ih_p, w_hh_b, P, c, y)
         return y
@@ -443,7 +444,8 @@ class _UniLSTMLayer(torch.autograd.Function):
             gemm([dA2[1:]], [y2], [g_hh], H4, H, T - 1, lda=H4, ldb=H, ldd=H, a_mn=True, b_mn=True, kbatches=B, a_batch_stride=T * H4,
                  b_batch_stride=T * H, out_f32=True, row_perm_H=H, split_k=1 if tiles >= 96 else max(1, min(4, 128 // tiles)))
         db = db_part.sum(0)                                                 # torch gate order already; both biases get it
-        return dx, g_ih, g_hh, db, db.clone(), None, None
+        pd = ctx.param_dtype                                                # float32 masters (or a module converted to bf16)
+        return dx, g_ih.to(pd), g_hh.to(pd), db.to(pd), db.to(pd).clone(), None, None
 
 
 def lstm_layer(x, w_ih, w_hh, b_ih, b_hh, training: bool, input_dropout=None):
