@@ -13,6 +13,7 @@ from __future__ import annotations
 import torch
 from torch import nn
 
+from .. import _lib as L
 from .. import lstm as plstm
 
 _instances = 0
@@ -43,6 +44,7 @@ class LSTM(nn.Module):
         return plstm.supported(x, self.hidden_size) if self.bidirectional else plstm.supported_uni(x, self.hidden_size)
 
     def forward(self, x, hx=None):
+        L.require_cuda(x)                                    # like every module of the package: CUDA tensors only, no CPU path
         if not self._persistent_ok(x, hx):
             flat = [getattr(self, n).to(x.dtype) for n in self._names]
             nd = 2 if self.bidirectional else 1

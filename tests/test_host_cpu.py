@@ -98,6 +98,23 @@ def test_no_cpu_fallback():
         d(torch.zeros(1, 3, 2), torch.zeros(1, 3, 8))
 
 
+def test_lstm_drop_in_and_decoder_entry_refuse_cpu_tensors():
+    """The torch.nn.LSTM drop-in keeps torch's parameter names (checkpoints load either way) and, like the rest of the package, has no
+    CPU path; neither has the label decoder."""
+    from ml_vae_b200._lib import MlvaeError
+    from ml_vae_b200.modules import LSTM
+    from ml_vae_b200.utils.decode_utils import decode_plvl_md_lbl_seqs_full
+    ref = torch.nn.LSTM(8, 32, 2, batch_first=True, dropout=0.15, bidirectional=True)
+    m = LSTM(input_size=8, hidden_size=32, num_layers=2, batch_first=True, dropout=0.15, bidirectional=True)
+    assert [n for n, _ in m.named_parameters()] == [n for n, _ in ref.named_parameters()]
+    m.load_state_dict(ref.state_dict())
+    with pytest.raises(MlvaeError, match="no CPU fallback"):
+        m(torch.zeros(2, 5, 8))
+    preds = {"phn_recog_out": torch.zeros(1, 6, 5), "boundary_v": torch.rand(1, 6), "pi_logits": torch.zeros(1, 6, 2)}
+    with pytest.raises(MlvaeError, match="no CPU fallback"):
+        decode_plvl_md_lbl_seqs_full(preds, ["a"], torch.tensor([1.0]), torch.zeros(1, 3, dtype=torch.long), torch.tensor([1.0]), torch.rand(5))
+
+
 def test_product_never_imports_oracle():
     """The oracle is test infrastructure: nothing under ml_vae_b200/ may import it."""
     for path in glob.glob(os.path.join(ROOT, "ml_vae_b200", "**", "*.py"), recursive=True):
