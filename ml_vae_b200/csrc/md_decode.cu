@@ -10,7 +10,7 @@
 // follow `numpy2`.
 //
 // One CTA per utterance, thread = phoneme l (both beta states), one __syncthreads per frame: dp[l-1, t-1, :] comes from a
-// double-buffered shared array, the emission gather log_p_yx[t, y_l, :] is prefetched one frame ahead, the 2 x 2-bit back
+// double-buffered shared array, the emission gather log_p_yx[t, y_l, :] is prefetched a chunk of four frames ahead, the 2 x 2-bit back
 // pointers of a (l, t) cell are one byte -- kept in shared memory when T x Lmax bytes fit (up to 226 KB: 20 s x 100 phonemes;
 // the backtrack is a chain of T dependent reads: ~30 cycles each from shared memory, an L2 round trip each from global
 // memory), in the caller's workspace otherwise.
@@ -34,8 +34,8 @@ struct DecodeParams {
 
 __device__ __forceinline__ double neg_inf() { return __longlong_as_double(0xfff0000000000000ull); }
 
-template <bool kPathInSmem>
-__global__ void __launch_bounds__(1024) md_decode_kernel(const DecodeParams p) {
+template <bool kPathInSmem, int kMaxThreads>
+__global__ void __launch_bounds__(kMaxThreads) md_decode_kernel(const DecodeParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int i = blockIdx.x, l = threadIdx.x;
     const int T = p.T, N = p.N, Lmax = p.Lmax;
@@ -87,40 +87,66 @@ __global__ void __launch_bounds__(1024) md_decode_kernel(const DecodeParams p) {
         s_dp[(0 * Lmax + l) * 2 + 0] = dp0;
         s_dp[(0 * Lmax + l) * 2 + 1] = dp1;
     }
-    float2 e_next = make_float2(0.f, 0.f), b_next = e_next, pi_next = e_next;
-    if (active && Ti > 1) { e_next = __ldg(lyx_row + (size_t)N); b_next = __ldg(lb + 1); pi_next = __ldg(lpi + 1); }
+    // The per-frame inputs are prefetched one CHUNK of kPf frames ahead (an L2 / HBM round trip is longer than a DP step: ~150 cycles of
+    // dependent float64 adds + one barrier), in registers with static indices.
+    constexpr int kPf = 4;
+    const float2 zero2 = make_float2(0.f, 0.f);
+    float2 e_cur[kPf], b_cur[kPf], pi_cur[kPf];
+#pragma unroll
+    for (int k = 0; k < kPf; ++k) {
+        const int t = 1 + k;
+        const bool ld = active && t < Ti;
+        e_cur[k] = ld ? __ldg(lyx_row + (size_t)t * N) : zero2;
+        b_cur[k] = ld ? __ldg(lb + t) : zero2;
+        pi_cur[k] = ld ? __ldg(lpi + t) : zero2;
+    }
     __syncthreads();
 
-    for (int t = 1; t < Ti; ++t) {
-        if (active) {
-            const float2 e = e_next, bb = b_next, pp = pi_next;
-            if (t + 1 < Ti) { e_next = __ldg(lyx_row + (size_t)(t + 1) * N); b_next = __ldg(lb + t + 1); pi_next = __ldg(lpi + t + 1); }
-            const double e0 = (double)e.x, e1 = (double)e.y, lb0 = (double)bb.x, lb1 = (double)bb.y;
-            // hold: dp[l, t-1, s] + log_p_b[t, 0] + log_p_yx[t, y_l, s] - log_p_y[y_l, s]
-            double v0 = __dsub_rn(__dadd_rn(__dadd_rn(dp0, lb0), e0), ly0);
-            double v1 = __dsub_rn(__dadd_rn(__dadd_rn(dp1, lb0), e1), ly1);
-            unsigned int c0 = 0, c1 = 0;
-            if (l > 0) {
-                const double *prev = s_dp + ((size_t)((t - 1) & 1) * Lmax + (l - 1)) * 2;
-                const double q0 = prev[0], q1 = prev[1];
-                double w0, w1;
-                if (p.numpy2) { w0 = (double)__fmul_rn(wf, pp.x); w1 = (double)__fmul_rn(wf, pp.y); }
-                else { w0 = __dmul_rn(p.weight, (double)pp.x); w1 = __dmul_rn(p.weight, (double)pp.y); }
-                const double a0 = __dadd_rn(q0, lb1), a1 = __dadd_rn(q1, lb1);
-                // value_list = [hold, from_correct, from_incorrect]; np.argmax: the first maximum wins
-                const double fc0 = __dsub_rn(__dadd_rn(__dadd_rn(a0, w0), e0), ly0), fi0 = __dsub_rn(__dadd_rn(__dadd_rn(a1, w0), e0), ly0);
-                const double fc1 = __dsub_rn(__dadd_rn(__dadd_rn(a0, w1), e1), ly1), fi1 = __dsub_rn(__dadd_rn(__dadd_rn(a1, w1), e1), ly1);
-                if (fc0 > v0) { v0 = fc0; c0 = 1; }
-                if (fi0 > v0) { v0 = fi0; c0 = 2; }
-                if (fc1 > v1) { v1 = fc1; c1 = 1; }
-                if (fi1 > v1) { v1 = fi1; c1 = 2; }
-            }
-            dp0 = v0; dp1 = v1;
-            double *cur = s_dp + ((size_t)(t & 1) * Lmax + l) * 2;
-            cur[0] = v0; cur[1] = v1;
-            path[(size_t)t * Lmax + l] = (unsigned char)(c0 | (c1 << 4));
+    for (int t0 = 1; t0 < Ti; t0 += kPf) {
+        float2 e_nxt[kPf], b_nxt[kPf], pi_nxt[kPf];
+#pragma unroll
+        for (int k = 0; k < kPf; ++k) {
+            const int t = t0 + kPf + k;
+            const bool ld = active && t < Ti;
+            e_nxt[k] = ld ? __ldg(lyx_row + (size_t)t * N) : zero2;
+            b_nxt[k] = ld ? __ldg(lb + t) : zero2;
+            pi_nxt[k] = ld ? __ldg(lpi + t) : zero2;
         }
-        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kPf; ++k) {
+            const int t = t0 + k;
+            if (t >= Ti) break;                                  // uniform over the CTA
+            if (active) {
+                const float2 e = e_cur[k], bb = b_cur[k], pp = pi_cur[k];
+                const double e0 = (double)e.x, e1 = (double)e.y, lb0 = (double)bb.x, lb1 = (double)bb.y;
+                // hold: dp[l, t-1, s] + log_p_b[t, 0] + log_p_yx[t, y_l, s] - log_p_y[y_l, s]
+                double v0 = __dsub_rn(__dadd_rn(__dadd_rn(dp0, lb0), e0), ly0);
+                double v1 = __dsub_rn(__dadd_rn(__dadd_rn(dp1, lb0), e1), ly1);
+                unsigned int c0 = 0, c1 = 0;
+                if (l > 0) {
+                    const double *prev = s_dp + ((size_t)((t - 1) & 1) * Lmax + (l - 1)) * 2;
+                    const double q0 = prev[0], q1 = prev[1];
+                    double w0, w1;
+                    if (p.numpy2) { w0 = (double)__fmul_rn(wf, pp.x); w1 = (double)__fmul_rn(wf, pp.y); }
+                    else { w0 = __dmul_rn(p.weight, (double)pp.x); w1 = __dmul_rn(p.weight, (double)pp.y); }
+                    const double a0 = __dadd_rn(q0, lb1), a1 = __dadd_rn(q1, lb1);
+                    // value_list = [hold, from_correct, from_incorrect]; np.argmax: the first maximum wins
+                    const double fc0 = __dsub_rn(__dadd_rn(__dadd_rn(a0, w0), e0), ly0), fi0 = __dsub_rn(__dadd_rn(__dadd_rn(a1, w0), e0), ly0);
+                    const double fc1 = __dsub_rn(__dadd_rn(__dadd_rn(a0, w1), e1), ly1), fi1 = __dsub_rn(__dadd_rn(__dadd_rn(a1, w1), e1), ly1);
+                    if (fc0 > v0) { v0 = fc0; c0 = 1; }
+                    if (fi0 > v0) { v0 = fi0; c0 = 2; }
+                    if (fc1 > v1) { v1 = fc1; c1 = 1; }
+                    if (fi1 > v1) { v1 = fi1; c1 = 2; }
+                }
+                dp0 = v0; dp1 = v1;
+                double *cur = s_dp + ((size_t)(t & 1) * Lmax + l) * 2;
+                cur[0] = v0; cur[1] = v1;
+                path[(size_t)t * Lmax + l] = (unsigned char)(c0 | (c1 << 4));
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int k = 0; k < kPf; ++k) { e_cur[k] = e_nxt[k]; b_cur[k] = b_nxt[k]; pi_cur[k] = pi_nxt[k]; }
     }
 
     // ---- backtrack (decode_utils.py:503-536): one thread, a chain of T_i dependent reads ----
@@ -182,12 +208,17 @@ int mlvae_md_decode(const float *d_log_p_yx, const float *d_log_p_b, const float
     const size_t dp_bytes = (size_t)4 * Lmax * sizeof(double);
     cudaStream_t st = (cudaStream_t)stream;
     MLVAE_CHECK_CUDA(cudaMemsetAsync(d_status, 0, (size_t)B * sizeof(int32_t), st));
+    // up to 256 phonemes (every real utterance) the kernel is compiled without the 64-register cap of a 1024-thread block
+    const bool small = threads <= 256;
     if (need == 0) {
         const size_t smem = dec_smem_bytes(T, Lmax);
-        MLVAE_CHECK_CUDA(cudaFuncSetAttribute(md_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDecSmemBudget));
-        md_decode_kernel<true><<<B, threads, smem, st>>>(p);
+        const void *fn = small ? (const void *)md_decode_kernel<true, 256> : (const void *)md_decode_kernel<true, 1024>;
+        MLVAE_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDecSmemBudget));
+        if (small) md_decode_kernel<true, 256><<<B, threads, smem, st>>>(p);
+        else md_decode_kernel<true, 1024><<<B, threads, smem, st>>>(p);
     } else {
-        md_decode_kernel<false><<<B, threads, dp_bytes, st>>>(p);
+        if (small) md_decode_kernel<false, 256><<<B, threads, dp_bytes, st>>>(p);
+        else md_decode_kernel<false, 1024><<<B, threads, dp_bytes, st>>>(p);
     }
     MLVAE_CHECK_CUDA(cudaGetLastError());
     return MLVAE_OK;
