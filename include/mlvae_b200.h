@@ -220,6 +220,12 @@ size_t mlvae_norm_state_bytes(int D);
 size_t mlvae_norm_scratch_bytes(int B, int D);
 int mlvae_global_norm(const float *d_x, const float *d_lens, int B, int T, int D, int training, int update_stats,
                       float *d_state, float *d_scratch, void *d_out, int out_dtype, void *stream);
+/* Data-parallel statistics (optional): the training-mode call above in two halves with the CALLER's all-reduce(sum) of
+ * d_avg {mean[D], std[D]} over the ranks in between, so that every rank keeps the running statistics of the GLOBAL batch (the
+ * reference under DDP would keep per-process statistics, models/test_vanilla_vae/model.py:24-25).  avg_scale = 1 / world. */
+int mlvae_global_norm_batch_avg(const float *d_x, const float *d_lens, int B, int T, int D, float *d_scratch, float *d_avg, void *stream);
+int mlvae_global_norm_from_avg(const float *d_x, int B, int T, int D, const float *d_avg, float avg_scale, int update_stats,
+                               float *d_state, void *d_out, int out_dtype, void *stream);
 
 /* ------------------------------------------------------------------------- *
  * Joint boundary / mispronunciation decoder (SURVEY 8f-4 "later"): the dynamic programme + backtrack of

@@ -88,6 +88,8 @@ SIGNATURES = {
     "mlvae_norm_state_bytes": (_sz, [_i]),
     "mlvae_norm_scratch_bytes": (_sz, [_i, _i]),
     "mlvae_global_norm": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp]),
+    "mlvae_global_norm_batch_avg": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "mlvae_global_norm_from_avg": (_i, [_vp, _i, _i, _i, _vp, C.c_float, _i, _vp, _vp, _i, _vp]),
     "mlvae_linear_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "mlvae_dense_bwd_scratch_bytes": (C.c_size_t, [_i]),
     "mlvae_dense_bwd_prep": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i64, C.c_float, _vp, _i, _vp]),

@@ -59,7 +59,9 @@ norm_stats_kernel(const float *__restrict__ x, const float *__restrict__ lens, i
 
 __global__ void __launch_bounds__(1024)
 norm_update_kernel(const float *__restrict__ mean_b, const float *__restrict__ std_b, int B, int D, int update,
-                   float *__restrict__ state) {
+                   float *__restrict__ state, float scale, float *__restrict__ avg_out) {
+    // scale: 1 / B (batch average) or 1 / world (rows = 1: the all-reduced sum of every rank's batch average).
+    // avg_out != nullptr: only write the average {mean[D], std[D]} there (data-parallel statistics exchange), leave the state alone.
     // state = {count, pad[3], glob_mean[D], glob_std[D]}.  Column c is summed by `groups` threads over interleaved
     // utterances, then combined in fixed group order (deterministic).
     extern __shared__ float s_red[];            // [2][groups][D]
@@ -77,7 +79,8 @@ norm_update_kernel(const float *__restrict__ mean_b, const float *__restrict__ s
     for (int col = threadIdx.x; col < D; col += blockDim.x) {
         float m = 0.f, sd = 0.f;
         for (int k = 0; k < groups; ++k) { m += s_red[k * D + col]; sd += s_red[(groups + k) * D + col]; }
-        m /= (float)B; sd /= (float)B;
+        m *= scale; sd *= scale;
+        if (avg_out) { avg_out[col] = m; avg_out[D + col] = sd; continue; }
         if (count == 0.f) { gm[col] = m; gs[col] = sd; }
         else if (update) {
             const float w = 1.f / (count + 1.f);
@@ -86,7 +89,7 @@ norm_update_kernel(const float *__restrict__ mean_b, const float *__restrict__ s
         }
     }
     __syncthreads();
-    if (threadIdx.x == 0) state[0] = count + 1.f;
+    if (threadIdx.x == 0 && !avg_out) state[0] = count + 1.f;
 }
 
 template <typename T>
@@ -125,9 +128,47 @@ int mlvae_global_norm(const float *d_x, const float *d_lens, int B, int T, int D
         const int groups = threads / D > 0 ? threads / D : 1;
         norm_stats_kernel<<<B, threads, sizeof(float) * groups * D, st>>>(d_x, d_lens, T, D, 1e-10f, mean_b, std_b);
         MLVAE_CHECK_CUDA(cudaGetLastError());
-        norm_update_kernel<<<1, threads, sizeof(float) * 2 * groups * D, st>>>(mean_b, std_b, B, D, update_stats, d_state);
+        norm_update_kernel<<<1, threads, sizeof(float) * 2 * groups * D, st>>>(mean_b, std_b, B, D, update_stats, d_state, 1.f / (float)B, nullptr);
         MLVAE_CHECK_CUDA(cudaGetLastError());
     }
+    const int64_t n = (int64_t)B * T * D;
+    int grid = (int)((n + kNormThreads - 1) / kNormThreads);
+    if (grid > sm_count() * 8) grid = sm_count() * 8;
+    if (out_dtype == MLVAE_F32) norm_apply_kernel<float><<<grid, kNormThreads, 0, st>>>(d_x, d_state, (int64_t)B * T, D, (float *)d_out);
+    else if (out_dtype == MLVAE_BF16) norm_apply_kernel<__nv_bfloat16><<<grid, kNormThreads, 0, st>>>(d_x, d_state, (int64_t)B * T, D, (__nv_bfloat16 *)d_out);
+    else return fail(MLVAE_ERR_INVALID_ARG, "unknown dtype %d", out_dtype);
+    MLVAE_CHECK_CUDA(cudaGetLastError());
+    return MLVAE_OK;
+}
+
+// Data-parallel variant in two calls with the caller's all-reduce in between ("optional second tiny all-reduce for
+// normalizer stats (2 D floats)"): every rank's batch contributes to ONE set of running statistics, as if the global batch had been seen.
+//   1. mlvae_global_norm_batch_avg: per-utterance statistics of this rank's batch, averaged -> d_avg {mean[D], std[D]}
+//   2. caller: all-reduce(sum) of d_avg over the ranks (equal batch sizes)
+//   3. mlvae_global_norm_from_avg: running update with avg_scale * d_avg (avg_scale = 1 / world), then (x - glob_mean) / glob_std
+int mlvae_global_norm_batch_avg(const float *d_x, const float *d_lens, int B, int T, int D, float *d_scratch, float *d_avg, void *stream) {
+    MLVAE_REQUIRE(d_x && d_lens && d_scratch && d_avg, MLVAE_ERR_INVALID_ARG, "global_norm_batch_avg: missing buffers");
+    MLVAE_REQUIRE(B > 0 && T > 0 && D > 0 && D <= 1024, MLVAE_ERR_INVALID_ARG, "global_norm_batch_avg: bad sizes (D <= 1024)");
+    cudaStream_t st = (cudaStream_t)stream;
+    float *mean_b = d_scratch, *std_b = d_scratch + (size_t)B * D;
+    const int threads = 1024;
+    const int groups = threads / D > 0 ? threads / D : 1;
+    norm_stats_kernel<<<B, threads, sizeof(float) * groups * D, st>>>(d_x, d_lens, T, D, 1e-10f, mean_b, std_b);
+    MLVAE_CHECK_CUDA(cudaGetLastError());
+    norm_update_kernel<<<1, threads, sizeof(float) * 2 * groups * D, st>>>(mean_b, std_b, B, D, 0, d_avg, 1.f / (float)B, d_avg);
+    MLVAE_CHECK_CUDA(cudaGetLastError());
+    return MLVAE_OK;
+}
+
+int mlvae_global_norm_from_avg(const float *d_x, int B, int T, int D, const float *d_avg, float avg_scale, int update_stats, float *d_state,
+                               void *d_out, int out_dtype, void *stream) {
+    MLVAE_REQUIRE(d_x && d_avg && d_state && d_out, MLVAE_ERR_INVALID_ARG, "global_norm_from_avg: missing buffers");
+    MLVAE_REQUIRE(B > 0 && T > 0 && D > 0 && D <= 1024 && avg_scale > 0.f, MLVAE_ERR_INVALID_ARG, "global_norm_from_avg: bad sizes (D <= 1024) or scale");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int threads = 1024;
+    const int groups = threads / D > 0 ? threads / D : 1;
+    norm_update_kernel<<<1, threads, sizeof(float) * 2 * groups * D, st>>>(d_avg, d_avg + D, 1, D, update_stats, d_state, avg_scale, nullptr);
+    MLVAE_CHECK_CUDA(cudaGetLastError());
     const int64_t n = (int64_t)B * T * D;
     int grid = (int)((n + kNormThreads - 1) / kNormThreads);
     if (grid > sm_count() * 8) grid = sm_count() * 8;

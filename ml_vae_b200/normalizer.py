@@ -19,12 +19,17 @@ from . import _lib as L
 
 class InputNormalization(torch.nn.Module):
     def __init__(self, mean_norm=True, std_norm=True, norm_type="global", avg_factor=None,
-                 requires_grad=False, update_until_epoch=3):
+                 requires_grad=False, update_until_epoch=3, sync_stats: bool = False, process_group=None):
         super().__init__()
         if norm_type != "global" or not (mean_norm and std_norm) or avg_factor is not None or requires_grad:
             raise NotImplementedError("only InputNormalization(norm_type='global') with SpeechBrain defaults "
                                       "(the reference's configuration, model.yaml:14-15) is implemented")
         self.update_until_epoch = update_until_epoch
+        # data parallel (optional): all-reduce the batch statistics (2 D floats) so that every rank keeps the
+        # running statistics of the GLOBAL batch; off by default = per-process statistics, what the reference does under DDP
+        self.sync_stats = bool(sync_stats)
+        self.process_group = process_group
+        self._avg = None
         self._state = None          # {count, pad[3], glob_mean[D], glob_std[D]} float32 on the device
         self._scratch = None
         self._dim = None
@@ -69,6 +74,19 @@ class InputNormalization(torch.nn.Module):
         out = torch.empty(B, T, D, dtype=out_dtype or x.dtype, device=x.device)
         if not self.training and self.count == 0:
             raise RuntimeError("InputNormalization(global) used in eval mode before any statistics were seen")
+        world = 1
+        if self.sync_stats and self.training and torch.distributed.is_available() and torch.distributed.is_initialized():
+            world = torch.distributed.get_world_size(self.process_group)
+        if world > 1:
+            if self._avg is None or self._avg.numel() != 2 * D or self._avg.device != x.device:
+                self._avg = torch.empty(2 * D, dtype=torch.float32, device=x.device)
+            L.check(L.lib().mlvae_global_norm_batch_avg(L.ptr(xf), L.ptr(lens), B, T, D, L.ptr(self._scratch), L.ptr(self._avg), L.stream_ptr()),
+                    "mlvae_global_norm_batch_avg", kernels=2)
+            torch.distributed.all_reduce(self._avg, op=torch.distributed.ReduceOp.SUM, group=self.process_group)
+            L.check(L.lib().mlvae_global_norm_from_avg(L.ptr(xf), B, T, D, L.ptr(self._avg), 1.0 / world, int(epoch < self.update_until_epoch),
+                                                       L.ptr(self._state), L.ptr(out), L.dtype_code(out), L.stream_ptr()),
+                    "mlvae_global_norm_from_avg", kernels=2)
+            return out
         L.check(L.lib().mlvae_global_norm(L.ptr(xf), L.ptr(lens), B, T, D, int(self.training),
                                           int(epoch < self.update_until_epoch), L.ptr(self._state), L.ptr(self._scratch),
                                           L.ptr(out), L.dtype_code(out), L.stream_ptr()), "mlvae_global_norm",

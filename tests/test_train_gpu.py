@@ -152,6 +152,45 @@ def test_normalizer_kernel_matches_oracle(cuda):
     assert b16.dtype == torch.bfloat16
 
 
+def test_normalizer_statistics_exchange_equals_the_global_batch(cuda):
+    """mlvae_global_norm_batch_avg -> all-reduce(sum) of the 2 D floats -> mlvae_global_norm_from_avg on every rank
+    gives every rank the running statistics and the outputs of ONE normaliser that saw the global batch.  Two "ranks" are simulated
+    on one device (the all-reduce is the sum of their two d_avg buffers)."""
+    from ml_vae_b200 import _lib as L
+    from ml_vae_b200.normalizer import InputNormalization
+    lib = L.lib()
+    g = torch.Generator().manual_seed(21)
+    whole = InputNormalization().to(cuda)
+    D, Bh = 24, 4
+    states = [torch.zeros(lib.mlvae_norm_state_bytes(D) // 4, device=cuda) for _ in range(2)]
+    for it, epoch in enumerate([0, 0, 1, 2, 4]):
+        T = 31 + it
+        x = (torch.randn(2 * Bh, T, D, generator=g) * (1 + it) + it).to(cuda)
+        n = torch.randint(2, T + 1, (2 * Bh,), generator=g); n[0] = T
+        lens = (n.float() / T).to(cuda)
+        want = whole(x, lens, epoch=epoch)
+        halves = [(x[r * Bh:(r + 1) * Bh].contiguous(), lens[r * Bh:(r + 1) * Bh].contiguous()) for r in range(2)]
+        avgs, scratch = [], torch.empty(2 * Bh * D, device=cuda)
+        for xr, lr in halves:
+            a = torch.empty(2 * D, device=cuda)
+            L.check(lib.mlvae_global_norm_batch_avg(L.ptr(xr), L.ptr(lr), Bh, T, D, L.ptr(scratch), L.ptr(a), L.stream_ptr()), "batch_avg")
+            avgs.append(a)
+        total = avgs[0] + avgs[1]                              # what all_reduce(SUM) leaves on every rank
+        for r, (xr, lr) in enumerate(halves):
+            out = torch.empty_like(xr)
+            L.check(lib.mlvae_global_norm_from_avg(L.ptr(xr), Bh, T, D, L.ptr(total), 0.5, int(epoch < 3), L.ptr(states[r]), L.ptr(out),
+                                                   L.F32, L.stream_ptr()), "from_avg")
+            assert_close(out, want[r * Bh:(r + 1) * Bh], FP32_RTOL, f"batch {it} rank {r}")
+    assert torch.equal(states[0], states[1])                   # identical running statistics on both ranks
+    assert float(states[0][0]) == whole.count
+    assert_close(states[0][4:4 + D], whole.glob_mean, FP32_RTOL, "running mean")
+    assert_close(states[0][4 + D:4 + 2 * D], whole.glob_std, FP32_RTOL, "running std")
+    # module switch: without an initialised process group it is the single-process normaliser
+    solo = InputNormalization(sync_stats=True).to(cuda)
+    ref2 = InputNormalization().to(cuda)
+    assert torch.equal(solo(x, lens, epoch=0), ref2(x, lens, epoch=0))
+
+
 def test_train_step_cuda_graph_replays_are_training_steps(cuda):
     """Captured step == eager step: same losses step by step (fresh eps each replay through the device counter,
     device-resident normaliser state, Adam)."""
