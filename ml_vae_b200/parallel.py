@@ -39,3 +39,23 @@ def broadcast_(flat_params: torch.Tensor, src: int = 0, group=None) -> torch.Ten
     if dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.broadcast(flat_params, src=src, group=group)
     return flat_params
+
+
+def valid_frame_count(rel_lens: torch.Tensor, T: int) -> torch.Tensor:
+    """Number of frames the reference's mask keeps (utils/data_utils.py:88: ``arange(T) < lens * T`` in float32), as a
+    float32 scalar on ``rel_lens``' device."""
+    t = torch.arange(T, device=rel_lens.device, dtype=torch.float32)
+    return (t[None, :] < (rel_lens.float()[:, None] * T)).sum().float()
+
+
+def global_batch_scale(rel_lens: torch.Tensor, T: int, world: int, group=None) -> torch.Tensor:
+    """Factor that turns this rank's length-masked MEAN loss into its share of the GLOBAL batch's masked mean once the gradients are
+    averaged over the ranks (optional): local mean = sum_r / cnt_r, global mean = sum_all / cnt_all, and the
+    average over ranks of  (world * cnt_r / cnt_all) * (sum_r / cnt_r)  is exactly sum_all / cnt_all.  One all-reduce of one float.
+    With equal numbers of valid frames on every rank the factor is 1."""
+    cnt = valid_frame_count(rel_lens, T)
+    if world <= 1:
+        return torch.ones_like(cnt)
+    tot = cnt.clone()
+    dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=group)
+    return cnt * float(world) / tot

@@ -151,7 +151,7 @@ class TrainStep:
     def __init__(self, fbank, normalizer, encoder, decoder, hparams: dict, lr: float = 1e-3,
                  compute_dtype=torch.bfloat16, max_grad_norm: float = 5.0, world_size: int = 1,
                  seed: int = 123456, overlap_all_reduce: bool = False, dp_mode: str = "auto",
-                 defer_weight_grads: bool = True):
+                 defer_weight_grads: bool = True, global_batch_mean: bool = False):
         """``dp_mode`` (world_size > 1): "peer" = gradient reduce-scatter + sharded clip/Adam + parameter all-gather by the two
         kernels of csrc/dp_optim.cu over NVLink peer memory; "nccl" = one NCCL all-reduce of the flat bucket, then the full
         Adam on every rank; "auto" = peer when the node's symmetric memory can be set up (all ranks agree), else nccl."""
@@ -159,6 +159,8 @@ class TrainStep:
         self.hparams = dict(hparams)
         self.dtype = compute_dtype
         self.world_size = world_size
+        # exact global-batch masked means under data parallel (optional; off = every rank's own masked mean, as DDP around the reference)
+        self.global_batch_mean = bool(global_batch_mean)
         self.max_grad_norm = max_grad_norm
         if dp_mode not in ("auto", "peer", "nccl"):
             raise ValueError(f"dp_mode must be 'auto', 'peer' or 'nccl', got {dp_mode!r}")
@@ -270,7 +272,11 @@ class TrainStep:
         eo = self.encoder(feats, lens=rel)
         do = self.decoder(eo["sampled_h"], feats, lens=rel)
         kld, rec = eo["kld_loss"], do["recon_loss"]
-        return self.w_kld * kld + self.w_rec * rec, kld, rec
+        loss = self.w_kld * kld + self.w_rec * rec
+        if self.global_batch_mean and self.world_size > 1:
+            from .parallel import global_batch_scale
+            loss = loss * global_batch_scale(rel, feats.shape[1], self.world_size)      # one all-reduce of one float
+        return loss, kld, rec
 
     # -- one training step ----------------------------------------------------------------
     def step_from_features(self, feats, rel):

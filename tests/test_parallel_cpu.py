@@ -65,6 +65,44 @@ def test_flat_bucket_all_reduce_equals_full_batch_gradient(tmp_path):
     assert got["in_bucket"] and abs(got["bucket_sum"] - float(ref.double().sum())) < 1e-5      # alignment gaps of the bucket stay zero
 
 
+def _scale_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ml_vae_b200.parallel import global_batch_scale, shard_batch, valid_frame_count
+    g = torch.Generator().manual_seed(5)
+    T, C = 37, 3
+    loss_elem = torch.rand(6, T, C, generator=g) + torch.arange(6.0)[:, None, None]      # unreduced (B, T, C) loss, a different level per utterance
+    lens = torch.tensor([1.0, 0.31, 0.5, 0.77, 0.12, 0.93])            # very different numbers of valid frames per rank
+    le, ln = shard_batch([loss_elem, lens], rank, world)
+    mask = (torch.arange(T)[None, :].float() < ln[:, None] * T).float()[..., None]
+    local_mean = (le * mask).sum() / (mask.sum() * C)                  # apply_lens_to_loss(..., 'mean') on this rank's utterances
+    f = global_batch_scale(ln, T, world)
+    contrib = torch.stack([f * local_mean, local_mean, valid_frame_count(ln, T)])
+    dist.all_reduce(contrib, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        torch.save({"scaled_mean_over_ranks": float(contrib[0] / world), "plain_mean_over_ranks": float(contrib[1] / world),
+                    "frames": float(contrib[2])}, out)
+    dist.destroy_process_group()
+
+
+def test_global_batch_scale_recovers_the_global_masked_mean(tmp_path):
+    """SURVEY 8e option: averaging (world * cnt_r / cnt_all) * local masked mean over the ranks IS the masked mean of the global batch
+    (utils/data_utils.py:67-104 on all utterances at once); the plain average of local means is not when the ranks hold different
+    numbers of valid frames."""
+    out = str(tmp_path / "s.pt")
+    mp.spawn(_scale_worker, args=(2, 29537, out), nprocs=2, join=True)
+    got = torch.load(out)
+    g = torch.Generator().manual_seed(5)
+    T, C = 37, 3
+    loss_elem = torch.rand(6, T, C, generator=g) + torch.arange(6.0)[:, None, None]
+    lens = torch.tensor([1.0, 0.31, 0.5, 0.77, 0.12, 0.93])
+    mask = (torch.arange(T)[None, :].float() < lens[:, None] * T).float()[..., None]
+    want = float((loss_elem * mask).sum() / (mask.sum() * C))
+    assert got["frames"] == float(mask.sum())
+    assert abs(got["scaled_mean_over_ranks"] - want) < 1e-5
+    assert abs(got["plain_mean_over_ranks"] - want) > 1e-3
+
+
 def test_flat_arena_keeps_names_values_and_views():
     from ml_vae_b200.modules import Decoder, VanillaVAE
     from ml_vae_b200.train_step import FlatArena
