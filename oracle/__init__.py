@@ -16,6 +16,11 @@ Parity pinning status (see DESIGN.md "Oracle"):
   ``/root/reference/src`` (with the tiny ``sb_shim`` standing in for the one
   SpeechBrain symbol they import).  The golden vectors it writes under
   ``tests/golden/`` are outputs of the reference code itself.
+* Joint boundary / mispronunciation decoder (``utils/decode_utils.py:374-565``): PINNED.
+  ``decode_ref.py`` restates the dynamic programme; ``oracle/gen_golden_decode.py`` runs the
+  reference FUNCTION itself (imported unmodified, numpy + joblib are installed here) on seeded
+  batches and asserts that the restatement reproduces its three integer outputs bit for bit
+  (``tests/golden/md_decode_cases.npz``).
 * Acoustic front-end (SpeechBrain ``Fbank``): PARITY UNPINNED.  The arithmetic
   lives in the third-party ``speechbrain`` package (requirements.txt:1,
   unpinned, 0.5.x by API usage) which is neither vendored in the reference
